@@ -1,0 +1,109 @@
+"""PointPillars decoration / scatter oracle (numpy, CPU).  TEST INFRASTRUCTURE.
+
+Restates the arithmetic of second/second/pytorch/models/pointpillars.py and
+voxel_encoder.py in numpy float32.  PINNED: oracle/gen_golden.py executes the
+reference's own classes (loaded by oracle/ref_loader.py) on seeded inputs and
+stores their outputs under tests/golden/; tests/test_oracle_pillar.py checks
+this restatement against them.
+
+Channel layouts produced (T = max points per pillar, all multiplied by the
+padding mask ``t < num[p]`` - voxel_encoder.py:27-48, pointpillars.py:226-231):
+
+  variant "pfn"            pointpillars.py:203-231   [x y z f.. | cx cy cz | px py | (dist)]
+  variant "old"            pointpillars.py:117-145   as "pfn" but channels 0,1 are
+                           overwritten with px,py (the aliasing bug)
+  variant "radius"         pointpillars.py:290-319   [r z f.. | cx cy cz | px py | (dist)]
+  variant "radius_height"  pointpillars.py:378-411   [r z f.. | cx cy cz | px py | h | (dist)]
+"""
+import numpy as np
+
+VARIANTS = ("pfn", "old", "radius", "radius_height")
+
+
+def paddings_indicator(actual_num, max_num):
+    """voxel_encoder.py:27-48 with axis=0: mask[p, t] = actual_num[p] > t."""
+    return np.asarray(actual_num).astype(np.int32)[:, None] > np.arange(max_num, dtype=np.int32)[None, :]
+
+
+def decorate(voxels, num_points, coors, voxel_size, pc_range, variant="pfn", with_distance=False):
+    """Decoration of (P,T,C) pillars -> (P,T,C') float32.
+
+    ``coors`` is (P,4) [batch, z, y, x] (preprocess.py:44-50).  The offsets are
+    Python floats exactly as the module computes them (pointpillars.py:198-201):
+    vx, vy and x_offset = vx/2 + pc_range[0] are *Python doubles*, multiplied into
+    float32 tensors -> torch rounds the scalar to float32 first.
+    """
+    f32 = np.float32
+    v = np.asarray(voxels, dtype=f32)
+    P, T, C = v.shape
+    num = np.asarray(num_points)
+    vx, vy = float(voxel_size[0]), float(voxel_size[1])
+    x_off = vx / 2 + float(pc_range[0])
+    y_off = vy / 2 + float(pc_range[1])
+    # pointpillars.py:208-210
+    mean = v[:, :, :3].sum(axis=1, keepdims=True, dtype=f32) / num.astype(f32).reshape(-1, 1, 1)
+    f_cluster = v[:, :, :3] - mean
+    # pointpillars.py:213-217
+    cx = coors[:, 3].astype(f32)[:, None] * f32(vx) + f32(x_off)
+    cy = coors[:, 2].astype(f32)[:, None] * f32(vy) + f32(y_off)
+    f_center = np.stack([v[:, :, 0] - cx, v[:, :, 1] - cy], axis=-1).astype(f32)
+    if variant == "pfn":
+        head = v
+    elif variant == "old":
+        head = v.copy()
+        head[:, :, :2] = f_center  # pointpillars.py:127-134: f_center is a view of features
+    elif variant in ("radius", "radius_height"):
+        r = np.sqrt(v[:, :, 0] * v[:, :, 0] + v[:, :, 1] * v[:, :, 1], dtype=f32)[..., None]
+        head = np.concatenate([r, v[:, :, 2:]], axis=-1)  # pointpillars.py:305-306
+    else:
+        raise ValueError(variant)
+    parts = [head, f_cluster, f_center]
+    if variant == "radius_height":
+        # pointpillars.py:387-393 (min/max over all T slots, padding zeros included)
+        h = v[:, :, 2:3].max(axis=1, keepdims=True) - v[:, :, 2:3].min(axis=1, keepdims=True)
+        parts.append(np.broadcast_to(h, (P, T, 1)).astype(f32))
+    if with_distance:
+        # "old": the norm is taken AFTER x,y were overwritten in place (pointpillars.py:127-139)
+        src = head if variant == "old" else v
+        d = np.sqrt((src[:, :, :3] * src[:, :, :3]).sum(axis=2, dtype=f32), dtype=f32)[..., None]
+        parts.append(d)
+    feats = np.concatenate(parts, axis=-1).astype(f32)
+    mask = paddings_indicator(num, T).astype(f32)[..., None]
+    return feats * mask
+
+
+def scatter(voxel_features, coords, batch_size, ny, nx):
+    """PointPillarsScatter.forward, pointpillars.py:444-476 -> (B,C,ny,nx)."""
+    feats = np.asarray(voxel_features)
+    C = feats.shape[1]
+    out = np.zeros((batch_size, C, ny * nx), dtype=feats.dtype)
+    for b in range(batch_size):
+        sel = coords[:, 0] == b
+        idx = coords[sel, 2].astype(np.int64) * nx + coords[sel, 3].astype(np.int64)
+        out[b][:, idx] = feats[sel].T
+    return out.reshape(batch_size, C, ny, nx)
+
+
+def simple_voxel_mean(voxels, num_points, num_input_features=4):
+    """SimpleVoxel.forward, voxel_encoder.py:219-225."""
+    v = np.asarray(voxels, dtype=np.float32)
+    return v[:, :, :num_input_features].sum(axis=1, dtype=np.float32) / \
+        np.asarray(num_points).astype(np.float32).reshape(-1, 1)
+
+
+def pfn_layer_eval(features, weight, bn_gamma, bn_beta, bn_mean, bn_var, eps=1e-3):
+    """PFNLayer.forward (last layer, use_norm, eval mode), pointpillars.py:51-65:
+    Linear(no bias) -> BatchNorm1d(eps=1e-3, running stats) -> ReLU -> max over T."""
+    x = features.astype(np.float32) @ weight.T.astype(np.float32)
+    x = (x - bn_mean) / np.sqrt(bn_var + np.float32(eps)) * bn_gamma + bn_beta
+    x = np.maximum(x, 0)
+    return x.max(axis=1).astype(np.float32)
+
+
+def merge_batch_coords(coords_list):
+    """merge_second_batch coordinate padding, second/second/data/preprocess.py:44-50:
+    prepend the batch index -> (sum V, 4) [b, z, y, x]."""
+    out = []
+    for i, c in enumerate(coords_list):
+        out.append(np.pad(c, ((0, 0), (1, 0)), mode="constant", constant_values=i))
+    return np.concatenate(out, axis=0)

@@ -1,0 +1,166 @@
+"""Hard-voxelizer oracle (CPU).  TEST INFRASTRUCTURE - see oracle/__init__.py.
+
+PARITY UNPINNED at the spconv boundary: the arithmetic of
+``spconv.utils.VoxelGeneratorV2`` is not in /root/reference.  The algorithm
+restated here is the in-tree sibling second/second/utils/simplevis.py:9-61,
+plus the output contract of second/second/data/preprocess.py:305-317.  The
+restatement IS pinned against that sibling: oracle/gen_golden.py executes the
+reference's ``points_to_bev`` on the bundled sweep and stores its density map;
+tests/test_oracle_voxel.py checks that this oracle's per-pillar counts and voxel
+count reproduce it (coordinate rule, bounds, first-come ids, ``break``).
+
+Two implementations of the same loop:
+  * ``points_to_voxel_loop``  - pure Python, a line-for-line walk of the
+    reference loop; small inputs only.
+  * ``points_to_voxel``       - the C restatement (oracle/voxel_oracle.c via
+    ctypes), checked against the loop version in the tests; this is also the
+    CPU baseline timed by bench.py.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libvoxel_oracle.so")
+_lib = None
+
+OVERFLOW_CONTINUE = 0
+OVERFLOW_BREAK = 1
+
+
+def build(force=False):
+    """gcc -O2 oracle/voxel_oracle.c -> oracle/libvoxel_oracle.so (git-ignored)."""
+    src = os.path.join(_HERE, "voxel_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fno-fast-math",
+                               "-o", _SO, src, "-lm"])
+    return _SO
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        lib = ctypes.CDLL(_SO)
+        lib.lvo_points_to_voxel.restype = ctypes.c_int32
+        lib.lvo_points_to_voxel.argtypes = [
+            ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.lvo_grid_size.restype = None
+        lib.lvo_grid_size.argtypes = [ctypes.c_void_p] * 3
+        lib.lvo_bev_counts.restype = None
+        lib.lvo_bev_counts.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def grid_size(voxel_size, coors_range):
+    """simplevis.py:27-30: np.round((hi - lo) / vs) in float32 -> int32, xyz."""
+    voxel_size = np.asarray(voxel_size, dtype=np.float32)
+    coors_range = np.asarray(coors_range, dtype=np.float32)
+    g = (coors_range[3:] - coors_range[:3]) / voxel_size
+    return np.round(g, 0, g).astype(np.int32)
+
+
+def points_to_voxel_loop(points, voxel_size, coors_range, max_points, max_voxels,
+                         overflow="continue"):
+    """Pure-Python walk of simplevis.py:35-51 with the voxel outputs of
+    preprocess.py:305-310.  Returns (voxels, coordinates, num_points_per_voxel)
+    sliced to voxel_num."""
+    points = np.ascontiguousarray(points, dtype=np.float32)
+    voxel_size = np.asarray(voxel_size, dtype=np.float32)
+    coors_range = np.asarray(coors_range, dtype=np.float32)
+    gs = grid_size(voxel_size, coors_range)
+    voxelmap_shape = tuple(int(v) for v in gs[::-1])
+    coor_to_voxelidx = -np.ones(shape=voxelmap_shape, dtype=np.int32)
+    N, C = points.shape
+    voxels = np.zeros((max_voxels, max_points, C), dtype=np.float32)
+    coors = np.zeros((max_voxels, 3), dtype=np.int32)
+    num = np.zeros((max_voxels,), dtype=np.int32)
+    coor = np.zeros(shape=(3,), dtype=np.int32)
+    voxel_num = 0
+    for i in range(N):
+        failed = False
+        for j in range(3):
+            c = np.floor((points[i, j] - coors_range[j]) / voxel_size[j])
+            if not (c >= 0) or c >= gs[j]:
+                failed = True
+                break
+            coor[2 - j] = c
+        if failed:
+            continue
+        voxelidx = coor_to_voxelidx[coor[0], coor[1], coor[2]]
+        if voxelidx == -1:
+            voxelidx = voxel_num
+            if voxel_num >= max_voxels:
+                if overflow == "break":
+                    break
+                continue
+            voxel_num += 1
+            coor_to_voxelidx[coor[0], coor[1], coor[2]] = voxelidx
+            coors[voxelidx] = coor
+        n = num[voxelidx]
+        if n < max_points:
+            voxels[voxelidx, n] = points[i]
+            num[voxelidx] += 1
+    return voxels[:voxel_num], coors[:voxel_num], num[:voxel_num]
+
+
+class VoxelOracle:
+    """Stateful C oracle that keeps the dense coor->voxelidx map between calls
+    (allocated once, touched cells reset - the spconv strategy)."""
+
+    def __init__(self, voxel_size, coors_range, max_points, max_voxels):
+        self.voxel_size = np.asarray(voxel_size, dtype=np.float32).copy()
+        self.coors_range = np.asarray(coors_range, dtype=np.float32).copy()
+        self.max_points = int(max_points)
+        self.max_voxels = int(max_voxels)
+        self.grid_size = grid_size(self.voxel_size, self.coors_range)
+        self._map = -np.ones(int(np.prod(self.grid_size.astype(np.int64))), dtype=np.int32)
+        self.last_kept_points = 0
+
+    def generate(self, points, max_voxels=None, overflow="continue", padded=False):
+        lib = _load()
+        points = np.ascontiguousarray(points, dtype=np.float32)
+        n, c = points.shape
+        mv = self.max_voxels if max_voxels is None else int(max_voxels)
+        voxels = np.zeros((mv, self.max_points, c), dtype=np.float32)
+        coors = np.zeros((mv, 3), dtype=np.int32)
+        num = np.zeros((mv,), dtype=np.int32)
+        kept = ctypes.c_int64(0)
+        vn = lib.lvo_points_to_voxel(
+            points.ctypes.data, n, c, self.voxel_size.ctypes.data, self.coors_range.ctypes.data,
+            self.max_points, mv, OVERFLOW_BREAK if overflow == "break" else OVERFLOW_CONTINUE,
+            self._map.ctypes.data, voxels.ctypes.data, coors.ctypes.data, num.ctypes.data,
+            ctypes.addressof(kept))
+        self.last_kept_points = kept.value
+        if padded:
+            return voxels, coors, num, vn
+        return voxels[:vn], coors[:vn], num[:vn]
+
+
+def points_to_voxel(points, voxel_size, coors_range, max_points, max_voxels,
+                    overflow="continue"):
+    """One-shot C oracle -> (voxels, coordinates, num_points_per_voxel)."""
+    return VoxelOracle(voxel_size, coors_range, max_points, max_voxels).generate(
+        points, overflow=overflow)
+
+
+def bev_counts_c(points_nx, shape, voxel_size, z_offset):
+    """C cross-check of oracle.bev_oracle.create_voxel_pointcloud (raw counts)."""
+    from . import bev_oracle
+    lib = _load()
+    pts = np.ascontiguousarray(points_nx, dtype=np.float32)
+    tm = bev_oracle.create_transformation_matrix_to_voxel_space(shape, voxel_size, (0, 0, z_offset))
+    m = np.ascontiguousarray(np.diag(tm)[:3], dtype=np.float64)
+    t = np.ascontiguousarray(tm[:3, 3], dtype=np.float64)
+    shp = np.asarray(shape, dtype=np.int32)
+    counts = np.zeros(tuple(int(s) for s in shape), dtype=np.uint32)
+    lib.lvo_bev_counts(pts.ctypes.data, pts.shape[0], pts.shape[1], m.ctypes.data,
+                       t.ctypes.data, shp.ctypes.data, counts.ctypes.data)
+    return counts
