@@ -1,0 +1,225 @@
+/* lyft_voxel.h - C ABI of the B200-native lidar voxelization / BEV rasterization
+ * engine (liblyftvoxel_b200.so, sm_100a only).
+ *
+ * The reference (jionie/Lyft-3D-Object-Detection) has no C/FFI plugin API on this
+ * path; its boundary is three Python surfaces.  Each entry point
+ * below names the reference interface it replaces (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ or torch types.
+ *   - Every function returns int: 0 = LV_OK, negative = LV_E_*.  lv_last_error()
+ *     returns a thread-local message.  Nothing aborts or throws across the ABI.
+ *   - "d_" pointers are device pointers on the handle's device, "h_" pointers are
+ *     host pointers.  The CALLER allocates every input and output; the library
+ *     owns only its workspace inside the handle (grown on first use / when a
+ *     larger problem arrives, never on a steady-state call).
+ *   - All work is enqueued on the caller's stream (a cudaStream_t passed as
+ *     void*); device-pointer entry points never synchronise.  Outputs are valid
+ *     once the caller synchronises that stream.  *_host entry points take host
+ *     buffers, do the H2D/D2H copies on the handle's stream and return after the
+ *     results are in the caller's host memory.
+ *   - A handle is bound to one device and is not thread-safe: one handle per
+ *     (process, device, stream).
+ *   - There is no CPU fallback: without a CUDA device lv_create fails with
+ *     LV_E_NODEVICE.
+ */
+#ifndef LYFT_VOXEL_H_
+#define LYFT_VOXEL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LV_OK 0
+#define LV_E_INVALID (-1)     /* bad argument (shape, null pointer, unsupported size) */
+#define LV_E_CUDA (-2)        /* a CUDA runtime call failed; see lv_last_error */
+#define LV_E_NOMEM (-3)       /* workspace allocation failed */
+#define LV_E_UNSUPPORTED (-4) /* feature not built / not supported on this device */
+#define LV_E_NODEVICE (-5)    /* no CUDA device / wrong architecture */
+
+#define LV_ABI_VERSION 1
+
+typedef struct lv_handle lv_handle;
+typedef void* lv_stream; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ lifecycle */
+
+int lv_abi_version(void);
+const char* lv_version_string(void);
+/* Number of visible CUDA devices (0 when none / no driver); never fails. */
+int lv_device_count(void);
+/* Creates a handle bound to `device` (must be compute capability 10.x). */
+int lv_create(int device, lv_handle** out);
+int lv_destroy(lv_handle* h);
+/* Thread-local message of the last failing call ("" if none).  h may be NULL. */
+const char* lv_last_error(lv_handle* h);
+/* Bytes of device workspace currently owned by the handle. */
+int64_t lv_workspace_bytes(lv_handle* h);
+/* Number of kernels this handle has launched since creation (bench.py's
+ * gpu_launches claim is read from here). */
+int64_t lv_launch_count(lv_handle* h);
+/* Pinned host memory for callers of the *_host entry points. */
+int lv_host_alloc(size_t bytes, void** out);
+int lv_host_free(void* p);
+/* Tuning knobs (0 = library default). */
+int lv_set_option(lv_handle* h, const char* name, int64_t value);
+
+/* ------------------------------------------------------------------ BEV rasteriser
+ *
+ * Replaces, per frame, the chain
+ *   LidarPointCloud.transform(car_from_sensor)      nuscenes-devkit/lyft_dataset_sdk/utils/data_classes.py:188-195
+ *   create_voxel_pointcloud(points, shape, voxel_size, z_offset)
+ *                                                   generating-dataset/generating_train_bev.py:84-101
+ *     (car_to_voxel_coords :73-82, transform_points :64-70,
+ *      create_transformation_matrix_to_voxel_space :47-62)
+ *   normalize_voxel_intensities(bev, max_intensity) generating-dataset/generating_train_bev.py:103-104
+ *   np.round(bev*255).astype(np.uint8)              generating-dataset/generating_train_bev.py:213
+ *   BEVImageDataset concat + /255 + HWC->CHW        deeplab_v3_baseline/dataset/dataset.py:83-106
+ *
+ * Points: `point_stride` float32 per point (x,y,z first; 4 for (N,4) arrays, 5
+ * for raw .bin sweeps).  They are grouped in `n_segments` consecutive segments
+ * (sweeps); segment s covers points [h_seg_offsets[s], h_seg_offsets[s+1]) and
+ * belongs to frame h_seg_frame[s] (NULL: segment s is frame s).  h_seg_tm (NULL:
+ * identity) holds one row-major float64 4x4 sensor->car transform per segment,
+ * applied in float64 and rounded to float32 exactly like PointCloud.transform.
+ *
+ * Arithmetic: u_k = fl64(fl64(m_k*p_k) + t_k) with
+ * m_k = 1/voxel_size[k], t = shape/2 + (0,0,z_offset)/voxel_size; c_k = trunc(u_k)
+ * (NOT floor); keep iff 0 <= c_k < shape[k]; bev[c_1, c_0, c_2] += 1.
+ * shape[0] must equal shape[1].
+ *
+ * Outputs (any may be NULL), each n_frames x ...:
+ *   d_raw   float32 (S0,S1,S2)  raw counts            (create_voxel_pointcloud)
+ *   d_norm  float32 (S0,S1,S2)  clip(raw/max_int,0,1) (normalize_voxel_intensities)
+ *   d_u8    uint8   (S0,S1,S2)  rint(norm*255)
+ *   d_chw   float32 (S2+3,S0,S1) [u8 | map]/255 in CHW; needs d_map_u8
+ *           (n_frames x (S0,S1,3) uint8) and S2 == 3.
+ */
+int lv_bev_rasterize(lv_handle* h, const float* d_points, int32_t point_stride,
+                     int32_t n_segments, const int64_t* h_seg_offsets,
+                     const int32_t* h_seg_frame, const double* h_seg_tm, int32_t n_frames,
+                     const int32_t shape[3], const double voxel_size[3], double z_offset,
+                     float max_intensity, float* d_raw, float* d_norm, uint8_t* d_u8,
+                     const uint8_t* d_map_u8, float* d_chw, lv_stream stream);
+
+/* Same, host buffers in and out (pinned memory from lv_host_alloc recommended).
+ * Copies points H2D, runs the kernels, copies every non-NULL output D2H, and
+ * returns after the handle's stream is idle. */
+int lv_bev_rasterize_host(lv_handle* h, const float* h_points, int32_t point_stride,
+                          int32_t n_segments, const int64_t* h_seg_offsets,
+                          const int32_t* h_seg_frame, const double* h_seg_tm, int32_t n_frames,
+                          const int32_t shape[3], const double voxel_size[3], double z_offset,
+                          float max_intensity, float* h_raw, float* h_norm, uint8_t* h_u8,
+                          const uint8_t* h_map_u8, float* h_chw);
+
+/* normalize_voxel_intensities alone (generating_train_bev.py:103-104) on a
+ * device array of n float32: out = clip(in / max_intensity, 0, 1). */
+int lv_bev_normalize(lv_handle* h, const float* d_in, int64_t n, float max_intensity,
+                     float* d_out, lv_stream stream);
+
+/* transform_points (generating-dataset/generating_train_bev.py:64-70) and
+ * car_to_voxel_coords (:73-82): out(3,N) float64 = (tm . [x;y;z;1])[:3], accumulated
+ * in k order with FMA from 0 (what the BLAS dgemm the reference calls does; for
+ * the diagonal voxel-space matrix this is the un-fused multiply-then-add of
+ * SURVEY.md Appendix A.1, bit for bit).  d_points is (N, point_stride) float32
+ * rows, h_tm16 a row-major float64 4x4 on the host, d_out 3 planes of N doubles. */
+int lv_transform_points(lv_handle* h, const float* d_points, int32_t point_stride, int64_t n,
+                        const double* h_tm16, double* d_out, lv_stream stream);
+
+/* ------------------------------------------------------------------ hard voxelizer
+ *
+ * Replaces spconv.utils.VoxelGeneratorV2.generate / generate_multi_gpu as called at
+ *   second/second/builder/voxel_builder.py:23-32      (constructor arguments)
+ *   second/second/data/preprocess.py:299-317           (generate, generate_multi_gpu)
+ *   second/second/inference.py:67-79                   (single-sample inference)
+ * and the legacy tuple API points_to_voxel (second/second/kittiviewer/viewer.py:389-396).
+ * Algorithm: the in-tree sibling second/second/utils/simplevis.py:9-61:
+ *   grid = rint((hi-lo)/vs) in float32; per point in index order
+ *   c_k = floorf((p_k - lo_k)/vs_k), reject unless 0 <= c_k < grid_k; coordinate
+ *   stored (z,y,x); voxel ids in order of first appearance, at most max_voxels;
+ *   a point is stored in slot num[id] iff num[id] < max_points.
+ */
+#define LV_OVERFLOW_CONTINUE 0 /* spconv >= 1.1: skip the point, keep scanning       */
+#define LV_OVERFLOW_BREAK 1    /* simplevis.py:48-49: stop at the first overflowing point */
+
+typedef struct lv_voxel_config {
+  float voxel_size[3];       /* x, y, z */
+  float coors_range[6];      /* xmin ymin zmin xmax ymax zmax */
+  int32_t max_points;        /* T: max points per voxel */
+  int32_t max_voxels;        /* V: max voxels per frame */
+  int32_t num_features;      /* C: float32 per point (>= 3) */
+  int32_t overflow_mode;     /* LV_OVERFLOW_* */
+  int32_t zero_tail;         /* 1: rows [voxel_num, max_voxels) are zero-filled
+                                (generate_multi_gpu padding, preprocess.py:311-317);
+                                0: they are left untouched (caller slices) */
+} lv_voxel_config;
+
+/* grid_size (x,y,z) for a config; pure host arithmetic. */
+int lv_voxel_grid_size(const lv_voxel_config* cfg, int32_t grid_xyz[3]);
+
+/* Voxelizes n_frames independent clouds.  Frame f covers points
+ * [h_frame_offsets[f], h_frame_offsets[f+1]) of d_points (row-major, C floats).
+ * Outputs are padded per frame:
+ *   d_voxels     float32 (n_frames, V, T, C)
+ *   d_coords     int32   (n_frames, V, 3)   zyx
+ *   d_num_points int32   (n_frames, V)
+ *   d_voxel_num  int32   (n_frames)
+ */
+int lv_voxelize(lv_handle* h, const lv_voxel_config* cfg, const float* d_points,
+                int32_t n_frames, const int64_t* h_frame_offsets, float* d_voxels,
+                int32_t* d_coords, int32_t* d_num_points, int32_t* d_voxel_num,
+                lv_stream stream);
+
+int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const float* h_points,
+                     int32_t n_frames, const int64_t* h_frame_offsets, float* h_voxels,
+                     int32_t* h_coords, int32_t* h_num_points, int32_t* h_voxel_num);
+
+/* ------------------------------------------------------------------ PointPillars
+ *
+ * lv_pillar_decorate replaces the decoration part of
+ *   PillarFeatureNet.forward             second/second/pytorch/models/pointpillars.py:203-231
+ *   PillarFeatureNetOld.forward          :117-145  (x,y aliasing kept)
+ *   PillarFeatureNetRadius.forward       :290-319
+ *   PillarFeatureNetRadiusHeight.forward :378-411
+ * including get_paddings_indicator (second/second/pytorch/models/voxel_encoder.py:27-48).
+ * Input d_voxels (P,T,C) float32, d_num_points (P) int32, d_coors (P,4) int32
+ * [batch,z,y,x]; output (P,T,C_out) float32, C_out = lv_pillar_out_channels().
+ * vx, vy, x_offset, y_offset are the module's scalars (pointpillars.py:198-201),
+ * already rounded to float32 the way torch rounds a Python scalar.
+ */
+#define LV_PILLAR_PFN 0
+#define LV_PILLAR_OLD 1
+#define LV_PILLAR_RADIUS 2
+#define LV_PILLAR_RADIUS_HEIGHT 3
+
+int lv_pillar_out_channels(int32_t num_features, int32_t variant, int32_t with_distance);
+
+int lv_pillar_decorate(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,
+                       const int32_t* d_coors, int64_t n_pillars, int32_t max_points,
+                       int32_t num_features, float vx, float vy, float x_offset,
+                       float y_offset, int32_t variant, int32_t with_distance, float* d_out,
+                       lv_stream stream);
+
+/* lv_pillar_scatter replaces PointPillarsScatter.forward
+ * (second/second/pytorch/models/pointpillars.py:444-476):
+ * canvas[b, c, y, x] = feats[p, c] for the pillar p with coords[p] = (b, ., y, x),
+ * 0 elsewhere.  d_feats (P,C) float32, d_coords (P,4) int32, canvas (B,C,ny,nx).
+ * Every canvas element is written exactly once (no separate memset). */
+int lv_pillar_scatter(lv_handle* h, const float* d_feats, const int32_t* d_coords,
+                      int64_t n_pillars, int32_t channels, int32_t batch_size, int32_t ny,
+                      int32_t nx, float* d_canvas, lv_stream stream);
+
+/* SimpleVoxel.forward (second/second/pytorch/models/voxel_encoder.py:219-225):
+ * out[p, c] = sum_t voxels[p, t, c] / num[p] for c < num_features_out. */
+int lv_voxel_mean(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,
+                  int64_t n_voxels, int32_t max_points, int32_t num_features,
+                  int32_t num_features_out, float* d_out, lv_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LYFT_VOXEL_H_ */

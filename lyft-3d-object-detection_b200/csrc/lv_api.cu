@@ -1,0 +1,184 @@
+// Handle lifecycle, error reporting and workspace management of the C ABI
+// (include/lyft_voxel.h).
+#include <stdarg.h>
+
+#include "lv_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void lv_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int lv_buffer::ensure(size_t bytes, cudaStream_t stream, int fill_byte, bool* grew) {
+  if (grew) *grew = false;
+  if (bytes <= cap && ptr != nullptr) return LV_OK;
+  if (bytes == 0) bytes = 256;
+  // growing: wait for anything that may still use the old allocation
+  if (ptr) {
+    LV_CHECK_CUDA(cudaStreamSynchronize(stream));
+    LV_CHECK_CUDA(cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+  }
+  size_t want = lv_align_up(bytes, 256);
+  cudaError_t e = cudaMalloc(&ptr, want);
+  if (e != cudaSuccess) {
+    ptr = nullptr;
+    lv_set_error("workspace cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    return LV_E_NOMEM;
+  }
+  cap = want;
+  if (fill_byte >= 0) LV_CHECK_CUDA(cudaMemsetAsync(ptr, fill_byte, want, stream));
+  if (grew) *grew = true;
+  return LV_OK;
+}
+
+void lv_buffer::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+
+int lv_mirror::sync(const void* src, size_t bytes, cudaStream_t stream, const void** out) {
+  bool same = host.size() == bytes && dev.ptr != nullptr && memcmp(host.data(), src, bytes) == 0;
+  if (!same) {
+    // `host` is pageable: cudaMemcpyAsync stages it before returning, so the
+    // vector may be overwritten by the next call without draining the stream.
+    LV_CHECK(dev.ensure(bytes, stream));
+    host.assign(static_cast<const unsigned char*>(src), static_cast<const unsigned char*>(src) + bytes);
+    LV_CHECK_CUDA(cudaMemcpyAsync(dev.ptr, host.data(), bytes, cudaMemcpyHostToDevice, stream));
+  }
+  *out = dev.ptr;
+  return LV_OK;
+}
+
+extern "C" {
+
+int lv_abi_version(void) { return LV_ABI_VERSION; }
+
+const char* lv_version_string(void) { return "lyftvoxel_b200 0.1.0 (sm_100a)"; }
+
+int lv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* lv_last_error(lv_handle*) { return g_err; }
+
+int lv_create(int device, lv_handle** out) {
+  if (!out) {
+    lv_set_error("lv_create: out is NULL");
+    return LV_E_INVALID;
+  }
+  *out = nullptr;
+  int n = lv_device_count();
+  if (n <= 0) {
+    lv_set_error("lv_create: no CUDA device visible (this library has no CPU fallback)");
+    return LV_E_NODEVICE;
+  }
+  if (device < 0 || device >= n) {
+    lv_set_error("lv_create: device %d out of range [0,%d)", device, n);
+    return LV_E_INVALID;
+  }
+  cudaDeviceProp prop;
+  LV_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    lv_set_error("lv_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                 device, prop.major, prop.minor);
+    return LV_E_NODEVICE;
+  }
+  LV_CHECK_CUDA(cudaSetDevice(device));
+  lv_handle* h = new lv_handle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    lv_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    return LV_E_CUDA;
+  }
+  *out = h;
+  return LV_OK;
+}
+
+int lv_destroy(lv_handle* h) {
+  if (!h) return LV_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  lv_buffer* bufs[] = {&h->bev_counts, &h->bev_seg_offsets.dev, &h->bev_seg_frame.dev, &h->bev_seg_tm.dev,
+                       &h->bev_stage_points, &h->bev_stage_out[0], &h->bev_stage_out[1], &h->bev_stage_out[2],
+                       &h->bev_stage_out[3], &h->bev_stage_out[4], &h->bev_stage_map,
+                       &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1],
+                       &h->vox_vals[0], &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state,
+                       &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_stage_points,
+                       &h->vox_stage_out[0], &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3],
+                       &h->pil_map};
+  for (lv_buffer* b : bufs) b->release();
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return LV_OK;
+}
+
+int64_t lv_workspace_bytes(lv_handle* h) {
+  if (!h) return 0;
+  lv_buffer* bufs[] = {&h->bev_counts, &h->bev_seg_offsets.dev, &h->bev_seg_frame.dev, &h->bev_seg_tm.dev,
+                       &h->bev_stage_points, &h->bev_stage_out[0], &h->bev_stage_out[1], &h->bev_stage_out[2],
+                       &h->bev_stage_out[3], &h->bev_stage_out[4], &h->bev_stage_map,
+                       &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1],
+                       &h->vox_vals[0], &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state,
+                       &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_stage_points,
+                       &h->vox_stage_out[0], &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3],
+                       &h->pil_map};
+  int64_t total = 0;
+  for (lv_buffer* b : bufs) total += (int64_t)b->cap;
+  return total;
+}
+
+int64_t lv_launch_count(lv_handle* h) { return h ? h->launches : 0; }
+
+int lv_host_alloc(size_t bytes, void** out) {
+  if (!out) {
+    lv_set_error("lv_host_alloc: out is NULL");
+    return LV_E_INVALID;
+  }
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    lv_set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return LV_E_NOMEM;
+  }
+  return LV_OK;
+}
+
+int lv_host_free(void* p) {
+  if (!p) return LV_OK;
+  LV_CHECK_CUDA(cudaFreeHost(p));
+  return LV_OK;
+}
+
+int lv_set_option(lv_handle* h, const char* name, int64_t value) {
+  if (!h || !name) {
+    lv_set_error("lv_set_option: null argument");
+    return LV_E_INVALID;
+  }
+  if (strcmp(name, "bev_frames_in_flight") == 0) {
+    h->bev_frames_in_flight = value;
+    return LV_OK;
+  }
+  if (strcmp(name, "vox_dense_map_limit_bytes") == 0) {
+    h->vox_dense_map_limit_bytes = value;
+    return LV_OK;
+  }
+  lv_set_error("lv_set_option: unknown option '%s'", name);
+  return LV_E_INVALID;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// Internal header shared by the kernels of liblyftvoxel_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lyft_voxel.h"
+
+#define LV_NUM_SMS_B200 148
+
+// ------------------------------------------------------------------ errors
+void lv_set_error(const char* fmt, ...);
+
+#define LV_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      lv_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return LV_E_CUDA;                                                                      \
+    }                                                                                        \
+  } while (0)
+
+#define LV_REQUIRE(cond, ...)     \
+  do {                            \
+    if (!(cond)) {                \
+      lv_set_error(__VA_ARGS__);  \
+      return LV_E_INVALID;        \
+    }                             \
+  } while (0)
+
+#define LV_CHECK(expr)          \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != LV_OK) return _r; \
+  } while (0)
+
+// ------------------------------------------------------------------ workspace
+// A growable device buffer owned by the handle.  ensure() reallocates only when
+// the request exceeds the capacity (never on a steady-state call); `fill` is the
+// byte the fresh allocation is initialised with (maps that must start "empty").
+struct lv_buffer {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes, cudaStream_t stream, int fill_byte = -1, bool* grew = nullptr);
+  void release();
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+// Host-side cache of a small table mirrored on the device (segment offsets,
+// transforms): re-uploaded only when the host content changes.
+struct lv_mirror {
+  lv_buffer dev;
+  std::vector<unsigned char> host;
+  // returns device pointer (uploaded on `stream` if the content changed)
+  int sync(const void* src, size_t bytes, cudaStream_t stream, const void** out);
+};
+
+struct lv_handle {
+  int device = 0;
+  int num_sms = LV_NUM_SMS_B200;
+  int64_t launches = 0;
+  cudaStream_t own_stream = nullptr;  // used by the *_host entry points
+
+  // options
+  int64_t bev_frames_in_flight = 0;   // 0 = auto
+  int64_t vox_dense_map_limit_bytes = 0;
+
+  // BEV
+  lv_buffer bev_counts;               // u32 [frames_in_flight][cells], kept all-zero between calls
+  lv_mirror bev_seg_offsets, bev_seg_frame, bev_seg_tm;
+  lv_buffer bev_stage_points, bev_stage_out[5], bev_stage_map;  // *_host staging
+
+  // voxelizer
+  lv_buffer vox_map;                  // i32 [frames_in_flight][grid cells], kept all-INT_MAX between calls
+  lv_buffer vox_cell, vox_aux, vox_keys[2], vox_vals[2], vox_hist, vox_chunk, vox_frame_state;
+  lv_mirror vox_frame_offsets, vox_chunk_table;
+  lv_buffer vox_stage_points, vox_stage_out[4];
+
+  // pillar
+  lv_buffer pil_map;                  // i32 [B][ny*nx]
+};
+
+inline size_t lv_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int64_t lv_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+#define LV_LAUNCH_CHECK(h)                 \
+  do {                                     \
+    (h)->launches += 1;                    \
+    LV_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 lv_ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void lv_st_stream_f4(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ unsigned lv_lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+#endif

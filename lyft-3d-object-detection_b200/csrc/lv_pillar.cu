@@ -1,0 +1,310 @@
+// PointPillars decoration, scatter and voxel-mean kernels (sm_100a).
+//
+// Replaces second/second/pytorch/models/pointpillars.py:203-231 (+ variants
+// :117-145, :290-319, :378-411), :444-476 and voxel_encoder.py:219-225.
+// Semantics in include/lyft_voxel.h and SURVEY.md Appendix A.3 / A.4.
+//
+// pillar_decorate_kernel  one warp per pillar, one CTA = 8 pillars.  The ~12 torch
+//   elementwise/reduce/cat kernels of the reference collapse into one pass: read
+//   (P,T,C) once (float4 per point when C == 4), write (P,T,C_out) once through a
+//   shared-memory stage so that the global stores are contiguous.
+//   Algorithmic bytes per pillar: T*C*4 + 20 read, T*C_out*4 written.
+// pillar_scatter_*        scatter-as-gather: pillars first drop their index into a
+//   dense cell->pillar map (kept all -1 between calls), then every canvas element
+//   is written exactly once by a tile kernel (128 cells x C channels per CTA) with
+//   128-bit streaming stores; the memset of the reference is fused away.
+//   Algorithmic bytes: P*(C*4+16) read, B*C*ny*nx*4 written.
+#include "lv_common.cuh"
+
+#define PIL_WARPS 8
+
+struct DecorateParams {
+  const float* voxels;
+  const int32_t* num;
+  const int32_t* coors;
+  int64_t P;
+  int T, C, C_out;
+  float vx, vy, x_off, y_off;
+  int variant, with_distance;
+  float* out;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <bool C4>
+__global__ void __launch_bounds__(PIL_WARPS * 32) pillar_decorate_kernel(DecorateParams p) {
+  extern __shared__ float stage[];  // [PIL_WARPS][T*C_out]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = p.T * p.C_out;
+  const int64_t pil0 = (int64_t)blockIdx.x * PIL_WARPS;
+  const int64_t pil = pil0 + warp;
+  float* my = stage + warp * per;
+  if (pil < p.P) {
+    const float* v = p.voxels + pil * p.T * p.C;
+    const int num = __ldg(p.num + pil);
+    // pass 1: sum of xyz over ALL T slots (padding zeros included), z range
+    float sx = 0.f, sy = 0.f, sz = 0.f, zmin = INFINITY, zmax = -INFINITY;
+    for (int t = lane; t < p.T; t += 32) {
+      float x, y, z;
+      if (C4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(v) + t);
+        x = q.x; y = q.y; z = q.z;
+      } else {
+        x = __ldg(v + t * p.C); y = __ldg(v + t * p.C + 1); z = __ldg(v + t * p.C + 2);
+      }
+      sx += x; sy += y; sz += z;
+      zmin = fminf(zmin, z); zmax = fmaxf(zmax, z);
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    const float fn = (float)num;
+    const float mx = __fdiv_rn(sx, fn), my_ = __fdiv_rn(sy, fn), mz = __fdiv_rn(sz, fn);  // :208-209
+    float height = 0.f;
+    if (p.variant == LV_PILLAR_RADIUS_HEIGHT) height = warp_max(zmax) - warp_min(zmin);     // :387-389
+    // pillar centre (:213-217): coors*vx + x_offset, separate multiply and add
+    const float cx = __fadd_rn(__fmul_rn((float)__ldg(p.coors + pil * 4 + 3), p.vx), p.x_off);
+    const float cy = __fadd_rn(__fmul_rn((float)__ldg(p.coors + pil * 4 + 2), p.vy), p.y_off);
+    // pass 2: emit
+    for (int t = lane; t < p.T; t += 32) {
+      float* o = my + t * p.C_out;
+      if (t >= num) {  // padding mask (:226-231)
+        for (int c = 0; c < p.C_out; ++c) o[c] = 0.f;
+        continue;
+      }
+      float f[8];
+      const int nf = p.C < 8 ? p.C : 8;
+      if (C4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(v) + t);
+        f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+      } else {
+        for (int c = 0; c < nf; ++c) f[c] = __ldg(v + t * p.C + c);
+      }
+      const float x = f[0], y = f[1], z = f[2];
+      const float px = x - cx, py = y - cy;
+      int k = 0;
+      if (p.variant == LV_PILLAR_PFN || p.variant == LV_PILLAR_OLD) {
+        const bool old = p.variant == LV_PILLAR_OLD;
+        o[k++] = old ? px : x;   // F7: Old overwrites x,y in place before the concat
+        o[k++] = old ? py : y;
+        o[k++] = z;
+        for (int c = 3; c < p.C; ++c) o[k++] = (c < 8) ? f[c] : __ldg(v + t * p.C + c);
+      } else {
+        o[k++] = sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));  // :303-306
+        o[k++] = z;
+        for (int c = 3; c < p.C; ++c) o[k++] = (c < 8) ? f[c] : __ldg(v + t * p.C + c);
+      }
+      o[k++] = x - mx; o[k++] = y - my_; o[k++] = z - mz;   // f_cluster (:210)
+      o[k++] = px; o[k++] = py;                             // f_center
+      if (p.variant == LV_PILLAR_RADIUS_HEIGHT) o[k++] = height;
+      if (p.with_distance) {
+        const float dx = (p.variant == LV_PILLAR_OLD) ? px : x, dy = (p.variant == LV_PILLAR_OLD) ? py : y;
+        o[k++] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(z, z)));
+      }
+    }
+  }
+  __syncthreads();
+  // contiguous write-out of the CTA's pillars
+  int64_t n_here = p.P - pil0;
+  if (n_here > PIL_WARPS) n_here = PIL_WARPS;
+  const int64_t total = n_here * per;
+  float* dst = p.out + pil0 * per;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = stage[i];
+}
+
+// ---------------------------------------------------------------- scatter
+__global__ void __launch_bounds__(256) pillar_index_kernel(const int32_t* __restrict__ coords, int64_t P, int B, int ny,
+                                                         int nx, int32_t* __restrict__ map) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int4 c = __ldg(reinterpret_cast<const int4*>(coords) + p);  // b, z, y, x
+  if (c.x < 0 || c.x >= B || c.z < 0 || c.z >= ny || c.w < 0 || c.w >= nx) return;
+  map[(int64_t)c.x * ny * nx + (int64_t)c.z * nx + c.w] = (int32_t)p;
+}
+
+#define SC_TILE 128
+#define SC_PAD 1
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) pillar_canvas_kernel(const float* __restrict__ feats, int32_t* __restrict__ map,
+                                                          int C, int64_t ncell, int tiles_per_sample,
+                                                          float* __restrict__ canvas) {
+  extern __shared__ float tile[];            // [C][SC_TILE + SC_PAD]
+  __shared__ int32_t idx[SC_TILE];
+  const int b = blockIdx.x / tiles_per_sample;
+  const int t = blockIdx.x - b * tiles_per_sample;
+  const int64_t cell0 = (int64_t)t * SC_TILE;
+  const int n_here = (int)((ncell - cell0) < SC_TILE ? (ncell - cell0) : SC_TILE);
+  int32_t* m = map + (int64_t)b * ncell + cell0;
+  int mine = -1;
+  if (threadIdx.x < SC_TILE) {
+    if ((int)threadIdx.x < n_here) {
+      mine = m[threadIdx.x];
+      if (mine >= 0) m[threadIdx.x] = -1;    // leave the map empty for the next call
+    }
+    idx[threadIdx.x] = mine;
+  }
+  const int any = __syncthreads_or(mine >= 0);
+  float* dst = canvas + (int64_t)b * C * ncell + cell0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (!any) {
+    // empty tile: pure streaming zero fill
+    for (int c = warp; c < C; c += 8) {
+      float* row = dst + (int64_t)c * ncell;
+      if (VEC && n_here == SC_TILE) {
+        lv_st_stream_f4(reinterpret_cast<float4*>(row) + lane, make_float4(0.f, 0.f, 0.f, 0.f));
+      } else {
+        for (int j = lane; j < n_here; j += 32) row[j] = 0.f;
+      }
+    }
+    return;
+  }
+  const int ld = SC_TILE + SC_PAD;
+  for (int i = threadIdx.x; i < C * ld; i += blockDim.x) tile[i] = 0.f;
+  __syncthreads();
+  for (int j = warp; j < n_here; j += 8) {
+    const int pi = idx[j];
+    if (pi < 0) continue;
+    const float* f = feats + (int64_t)pi * C;
+    for (int c = lane; c < C; c += 32) tile[c * ld + j] = __ldg(f + c);
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += 8) {
+    float* row = dst + (int64_t)c * ncell;
+    const float* s = tile + c * ld;
+    if (VEC && n_here == SC_TILE) {
+      lv_st_stream_f4(reinterpret_cast<float4*>(row) + lane,
+                      make_float4(s[4 * lane], s[4 * lane + 1], s[4 * lane + 2], s[4 * lane + 3]));
+    } else {
+      for (int j = lane; j < n_here; j += 32) row[j] = s[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- voxel mean
+__global__ void __launch_bounds__(256) voxel_mean_kernel(const float* __restrict__ voxels, const int32_t* __restrict__ num,
+                                                       int64_t P, int T, int C, int Cout, float* __restrict__ out) {
+  // one thread per (voxel, channel): T is small (5) for the SECOND configs
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * Cout) return;
+  const int64_t p = i / Cout;
+  const int c = (int)(i - p * Cout);
+  const float* v = voxels + p * T * C + c;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += __ldg(v + t * C);
+  out[i] = __fdiv_rn(s, (float)__ldg(num + p));
+}
+
+extern "C" int lv_pillar_out_channels(int32_t num_features, int32_t variant, int32_t with_distance) {
+  if (num_features < 3) return LV_E_INVALID;
+  int c;
+  switch (variant) {
+    case LV_PILLAR_PFN:
+    case LV_PILLAR_OLD: c = num_features + 5; break;             // pointpillars.py:176 / :90
+    case LV_PILLAR_RADIUS: c = num_features + 5 - 1; break;      // :262-263
+    case LV_PILLAR_RADIUS_HEIGHT: c = num_features + 6 - 1; break;  // :350-351
+    default: return LV_E_INVALID;
+  }
+  return c + (with_distance ? 1 : 0);
+}
+
+extern "C" int lv_pillar_decorate(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,
+                                  const int32_t* d_coors, int64_t n_pillars, int32_t max_points,
+                                  int32_t num_features, float vx, float vy, float x_offset, float y_offset,
+                                  int32_t variant, int32_t with_distance, float* d_out, lv_stream stream_) {
+  LV_REQUIRE(h != nullptr, "lv_pillar_decorate: null handle");
+  LV_REQUIRE(n_pillars >= 0 && max_points > 0, "lv_pillar_decorate: bad sizes");
+  const int c_out = lv_pillar_out_channels(num_features, variant, with_distance);
+  LV_REQUIRE(c_out > 0, "lv_pillar_decorate: bad num_features %d / variant %d", num_features, variant);
+  if (n_pillars == 0) return LV_OK;
+  LV_REQUIRE(d_voxels && d_num_points && d_coors && d_out, "lv_pillar_decorate: null pointer");
+  LV_REQUIRE((reinterpret_cast<uintptr_t>(d_coors) & 15) == 0, "lv_pillar_decorate: coors must be 16-byte aligned");
+  LV_CHECK_CUDA(cudaSetDevice(h->device));
+  DecorateParams p{d_voxels, d_num_points, d_coors, n_pillars, max_points, num_features, c_out,
+                   vx, vy, x_offset, y_offset, variant, with_distance ? 1 : 0, d_out};
+  const size_t smem = (size_t)PIL_WARPS * max_points * c_out * sizeof(float);
+  LV_REQUIRE(smem <= 200 * 1024, "lv_pillar_decorate: max_points*channels too large for the shared-memory stage");
+  const int64_t grid = lv_div_up(n_pillars, PIL_WARPS);
+  LV_REQUIRE(grid < (1ll << 31), "lv_pillar_decorate: too many pillars");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool c4 = num_features == 4 && (reinterpret_cast<uintptr_t>(d_voxels) & 15) == 0;
+  if (c4) {
+    if (smem > 48 * 1024)
+      LV_CHECK_CUDA(cudaFuncSetAttribute(pillar_decorate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pillar_decorate_kernel<true><<<(unsigned)grid, PIL_WARPS * 32, smem, stream>>>(p);
+  } else {
+    if (smem > 48 * 1024)
+      LV_CHECK_CUDA(cudaFuncSetAttribute(pillar_decorate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pillar_decorate_kernel<false><<<(unsigned)grid, PIL_WARPS * 32, smem, stream>>>(p);
+  }
+  LV_LAUNCH_CHECK(h);
+  return LV_OK;
+}
+
+extern "C" int lv_pillar_scatter(lv_handle* h, const float* d_feats, const int32_t* d_coords, int64_t n_pillars,
+                                 int32_t channels, int32_t batch_size, int32_t ny, int32_t nx, float* d_canvas,
+                                 lv_stream stream_) {
+  LV_REQUIRE(h != nullptr, "lv_pillar_scatter: null handle");
+  LV_REQUIRE(n_pillars >= 0 && channels > 0 && batch_size >= 0 && ny > 0 && nx > 0, "lv_pillar_scatter: bad sizes");
+  if (batch_size == 0) return LV_OK;
+  LV_REQUIRE(d_canvas != nullptr, "lv_pillar_scatter: null canvas");
+  LV_REQUIRE(n_pillars == 0 || (d_feats && d_coords), "lv_pillar_scatter: null pointer");
+  LV_REQUIRE(n_pillars < (1ll << 31), "lv_pillar_scatter: too many pillars");
+  LV_REQUIRE((reinterpret_cast<uintptr_t>(d_coords) & 15) == 0, "lv_pillar_scatter: coords must be 16-byte aligned");
+  LV_CHECK_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t ncell = (int64_t)ny * nx;
+  LV_CHECK(h->pil_map.ensure((size_t)batch_size * ncell * sizeof(int32_t), stream, 0xff));
+  if (n_pillars > 0) {
+    pillar_index_kernel<<<(unsigned)lv_div_up(n_pillars, 256), 256, 0, stream>>>(d_coords, n_pillars, batch_size, ny, nx,
+                                                                               h->pil_map.as<int32_t>());
+    LV_LAUNCH_CHECK(h);
+  }
+  const int tiles = (int)lv_div_up(ncell, SC_TILE);
+  const size_t smem = (size_t)channels * (SC_TILE + SC_PAD) * sizeof(float);
+  LV_REQUIRE(smem <= 200 * 1024, "lv_pillar_scatter: too many channels (%d)", channels);
+  const bool vec = (ncell % 4 == 0) && (reinterpret_cast<uintptr_t>(d_canvas) & 15) == 0;
+  const int64_t grid = (int64_t)tiles * batch_size;
+  LV_REQUIRE(grid < (1ll << 31), "lv_pillar_scatter: canvas too large");
+  if (vec) {
+    if (smem > 48 * 1024)
+      LV_CHECK_CUDA(cudaFuncSetAttribute(pillar_canvas_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pillar_canvas_kernel<true><<<(unsigned)grid, 256, smem, stream>>>(d_feats, h->pil_map.as<int32_t>(), channels, ncell,
+                                                                    tiles, d_canvas);
+  } else {
+    if (smem > 48 * 1024)
+      LV_CHECK_CUDA(cudaFuncSetAttribute(pillar_canvas_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pillar_canvas_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(d_feats, h->pil_map.as<int32_t>(), channels, ncell,
+                                                                     tiles, d_canvas);
+  }
+  LV_LAUNCH_CHECK(h);
+  return LV_OK;
+}
+
+extern "C" int lv_voxel_mean(lv_handle* h, const float* d_voxels, const int32_t* d_num_points, int64_t n_voxels,
+                             int32_t max_points, int32_t num_features, int32_t num_features_out, float* d_out,
+                             lv_stream stream_) {
+  LV_REQUIRE(h != nullptr, "lv_voxel_mean: null handle");
+  LV_REQUIRE(n_voxels >= 0 && max_points > 0 && num_features > 0 && num_features_out > 0 &&
+                 num_features_out <= num_features, "lv_voxel_mean: bad sizes");
+  if (n_voxels == 0) return LV_OK;
+  LV_REQUIRE(d_voxels && d_num_points && d_out, "lv_voxel_mean: null pointer");
+  LV_CHECK_CUDA(cudaSetDevice(h->device));
+  const int64_t items = n_voxels * num_features_out;
+  voxel_mean_kernel<<<(unsigned)lv_div_up(items, 256), 256, 0, (cudaStream_t)stream_>>>(
+      d_voxels, d_num_points, n_voxels, max_points, num_features, num_features_out, d_out);
+  LV_LAUNCH_CHECK(h);
+  return LV_OK;
+}

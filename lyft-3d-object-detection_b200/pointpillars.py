@@ -1,0 +1,291 @@
+"""PointPillars drop-ins: decoration + scatter on the B200 kernels.
+
+Mirrors second/second/pytorch/models/pointpillars.py and the registry of
+voxel_encoder.py / middle.py: same class names, constructor
+arguments, ``forward`` signatures and ``state_dict`` keys
+(``pfn_layers.{i}.linear.weight``, ``pfn_layers.{i}.norm.*``) so reference
+checkpoints load and ``module_class_name`` in a config resolves unchanged.
+
+  PillarFeatureNet / ...Old / ...Radius / ...RadiusHeight
+      decoration (mean offset, pillar-centre offset, padding mask, variants) is ONE
+      fused CUDA kernel (lv_pillar_decorate); the PFNLayer (Linear 9->64 + BN +
+      ReLU + max) stays in PyTorch exactly as in the reference.
+  PointPillarsScatter
+      scatter-as-gather CUDA kernel (lv_pillar_scatter), differentiable w.r.t.
+      ``voxel_features`` (the backward is a torch gather of the canvas gradient).
+  SimpleVoxel / SimpleVoxelRadius  (voxel_encoder.py:207-255) via lv_voxel_mean.
+
+CUDA float32 tensors only; anything else raises - there is no CPU path.
+"""
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _native as nat
+
+REGISTERED_VFE_CLASSES = {}
+REGISTERED_MIDDLE_CLASSES = {}
+
+
+def register_vfe(cls, name=None):
+    """voxel_encoder.py:13-19."""
+    if name is None:
+        name = cls.__name__
+    assert name not in REGISTERED_VFE_CLASSES, f"exist class: {REGISTERED_VFE_CLASSES}"
+    REGISTERED_VFE_CLASSES[name] = cls
+    return cls
+
+
+def get_vfe_class(name):
+    """voxel_encoder.py:21-24."""
+    assert name in REGISTERED_VFE_CLASSES, f"available class: {REGISTERED_VFE_CLASSES}"
+    return REGISTERED_VFE_CLASSES[name]
+
+
+def register_middle(cls, name=None):
+    """middle.py:17-23."""
+    if name is None:
+        name = cls.__name__
+    assert name not in REGISTERED_MIDDLE_CLASSES, f"exist class: {REGISTERED_MIDDLE_CLASSES}"
+    REGISTERED_MIDDLE_CLASSES[name] = cls
+    return cls
+
+
+def get_middle_class(name):
+    """middle.py:25-28."""
+    assert name in REGISTERED_MIDDLE_CLASSES, f"available class: {REGISTERED_MIDDLE_CLASSES}"
+    return REGISTERED_MIDDLE_CLASSES[name]
+
+
+def get_paddings_indicator(actual_num, max_num, axis=0):
+    """voxel_encoder.py:27-48 (kept for callers; the kernels apply the mask themselves)."""
+    actual_num = torch.unsqueeze(actual_num, axis + 1)
+    shape = [1] * len(actual_num.shape)
+    shape[axis + 1] = -1
+    steps = torch.arange(max_num, dtype=torch.int, device=actual_num.device).view(shape)
+    return actual_num.int() > steps
+
+
+def _require_cuda_f32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise nat.LyftVoxelError(nat.LV_E_NODEVICE, "%s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise nat.LyftVoxelError(nat.LV_E_INVALID, "%s must be float32, got %s" % (name, t.dtype))
+
+
+def _f32(x):
+    """Round a Python scalar the way torch does when it meets a float32 tensor."""
+    return float(np.float32(x))
+
+
+def decorate_pillars(features, num_voxels, coors, vx, vy, x_offset, y_offset, variant="pfn",
+                     with_distance=False):
+    """Fused decoration: (P,T,C) float32 -> (P,T,C_out) float32, padding rows zero.
+    pointpillars.py:203-231 (+ :117-145, :290-319, :378-411)."""
+    _require_cuda_f32(features, "features")
+    lib = nat.load()
+    features = features.contiguous()
+    P, T, C = features.shape
+    num = num_voxels.to(torch.int32).contiguous()
+    co = coors.to(torch.int32).contiguous()
+    v = nat.PILLAR_VARIANTS[variant]
+    c_out = lib.lv_pillar_out_channels(C, v, int(bool(with_distance)))
+    if c_out <= 0:
+        raise nat.LyftVoxelError(nat.LV_E_INVALID, "bad num_features %d" % C)
+    out = torch.empty((P, T, c_out), dtype=torch.float32, device=features.device)
+    h = nat.get_handle(features.device.index)
+    with torch.cuda.device(features.device):
+        nat.check(lib.lv_pillar_decorate(h.ptr, features.data_ptr(), num.data_ptr(), co.data_ptr(), P, T, C,
+                                         _f32(vx), _f32(vy), _f32(x_offset), _f32(y_offset), v,
+                                         int(bool(with_distance)), out.data_ptr(),
+                                         nat.current_stream_ptr(features.device)))
+    return out
+
+
+class PFNLayer(nn.Module):
+    """pointpillars.py:17-65 - unchanged PyTorch layer (Linear, BatchNorm1d eps=1e-3
+    momentum=0.01, ReLU, max over the points of a pillar)."""
+
+    def __init__(self, in_channels, out_channels, use_norm=True, last_layer=False):
+        super().__init__()
+        self.name = 'PFNLayer'
+        self.last_vfe = last_layer
+        if not self.last_vfe:
+            out_channels = out_channels // 2
+        self.units = out_channels
+        self.linear = nn.Linear(in_channels, self.units, bias=not use_norm)
+        self.norm = nn.BatchNorm1d(self.units, eps=1e-3, momentum=0.01) if use_norm else nn.Identity()
+
+    def forward(self, inputs):
+        x = self.linear(inputs)
+        x = self.norm(x.permute(0, 2, 1).contiguous()).permute(0, 2, 1).contiguous()
+        x = F.relu(x)
+        x_max = torch.max(x, dim=1, keepdim=True)[0]
+        if self.last_vfe:
+            return x_max
+        return torch.cat([x, x_max.repeat(1, inputs.shape[1], 1)], dim=2)
+
+
+class _PillarFeatureNetBase(nn.Module):
+    _variant = "pfn"
+    _extra = 5          # channels added by the decoration (before with_distance)
+    _name = "PillarFeatureNet"
+
+    def __init__(self, num_input_features=4, use_norm=True, num_filters=(64,), with_distance=False,
+                 voxel_size=(0.2, 0.2, 4), pc_range=(0, -40, -3, 70.4, 40, 1)):
+        super().__init__()
+        self.name = self._name
+        assert len(num_filters) > 0
+        num_input_features += self._extra
+        if with_distance:
+            num_input_features += 1
+        self._with_distance = with_distance
+        num_filters = [num_input_features] + list(num_filters)
+        layers = []
+        for i in range(len(num_filters) - 1):
+            layers.append(PFNLayer(num_filters[i], num_filters[i + 1], use_norm,
+                                   last_layer=(i >= len(num_filters) - 2)))
+        self.pfn_layers = nn.ModuleList(layers)
+        # pointpillars.py:198-201
+        self.vx = voxel_size[0]
+        self.vy = voxel_size[1]
+        self.x_offset = self.vx / 2 + pc_range[0]
+        self.y_offset = self.vy / 2 + pc_range[1]
+
+    def decorate(self, features, num_voxels, coors):
+        return decorate_pillars(features, num_voxels, coors, self.vx, self.vy, self.x_offset, self.y_offset,
+                                variant=self._variant, with_distance=self._with_distance)
+
+    def forward(self, features, num_voxels, coors):
+        features = self.decorate(features, num_voxels, coors)
+        for pfn in self.pfn_layers:
+            features = pfn(features)
+        return features.squeeze()
+
+
+@register_vfe
+class PillarFeatureNetOld(_PillarFeatureNetBase):
+    """pointpillars.py:68-151 (keeps the x,y aliasing of :127-134)."""
+    _variant = "old"
+    _name = "PillarFeatureNetOld"
+
+
+@register_vfe
+class PillarFeatureNet(_PillarFeatureNetBase):
+    """pointpillars.py:154-237.  (The reference defines this class without
+    @register_vfe and sets name 'PillarFeatureNetOld'; the Lyft configs select it
+    by module_class_name, so it is registered here.)"""
+    _variant = "pfn"
+    _name = "PillarFeatureNet"
+
+
+@register_vfe
+class PillarFeatureNetRadius(_PillarFeatureNetBase):
+    """pointpillars.py:240-325."""
+    _variant = "radius"
+    _extra = 4
+    _name = "PillarFeatureNetRadius"
+
+
+@register_vfe
+class PillarFeatureNetRadiusHeight(_PillarFeatureNetBase):
+    """pointpillars.py:328-417."""
+    _variant = "radius_height"
+    _extra = 5
+    _name = "PillarFeatureNetRadiusHeight"
+
+
+class _ScatterFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, voxel_features, coords, batch_size, ny, nx):
+        lib = nat.load()
+        feats = voxel_features.contiguous()
+        co = coords.to(torch.int32).contiguous()
+        P, C = feats.shape
+        canvas = torch.empty((batch_size, C, ny, nx), dtype=torch.float32, device=feats.device)
+        h = nat.get_handle(feats.device.index)
+        with torch.cuda.device(feats.device):
+            nat.check(lib.lv_pillar_scatter(h.ptr, feats.data_ptr(), co.data_ptr(), P, C, batch_size, ny, nx,
+                                            canvas.data_ptr(), nat.current_stream_ptr(feats.device)))
+        ctx.save_for_backward(co)
+        ctx.dims = (ny, nx)
+        return canvas
+
+    @staticmethod
+    def backward(ctx, grad):
+        (co,) = ctx.saved_tensors
+        co = co.long()
+        g = grad[co[:, 0], :, co[:, 2], co[:, 3]]
+        return g, None, None, None, None
+
+
+def scatter_pillars(voxel_features, coords, batch_size, ny, nx):
+    """canvas[b,:,y,x] = voxel_features[p] for coords[p] = (b,.,y,x); zeros elsewhere."""
+    _require_cuda_f32(voxel_features, "voxel_features")
+    return _ScatterFn.apply(voxel_features, coords, int(batch_size), int(ny), int(nx))
+
+
+@register_middle
+class PointPillarsScatter(nn.Module):
+    """pointpillars.py:420-476."""
+
+    def __init__(self, output_shape, use_norm=True, num_input_features=64, num_filters_down1=[64],
+                 num_filters_down2=[64, 64], name='SpMiddle2K'):
+        super().__init__()
+        self.name = 'PointPillarsScatter'
+        self.output_shape = output_shape
+        self.ny = output_shape[2]
+        self.nx = output_shape[3]
+        self.nchannels = num_input_features
+
+    def forward(self, voxel_features, coords, batch_size):
+        if voxel_features.dtype != torch.float32:
+            # fp16 under apex O2 (train.py:223-228): compute in fp32, return the input dtype
+            return scatter_pillars(voxel_features.float(), coords, batch_size, self.ny, self.nx).to(
+                voxel_features.dtype)
+        return scatter_pillars(voxel_features, coords, batch_size, self.ny, self.nx)
+
+
+def voxel_mean(features, num_voxels, num_input_features):
+    _require_cuda_f32(features, "features")
+    lib = nat.load()
+    features = features.contiguous()
+    P, T, C = features.shape
+    num = num_voxels.to(torch.int32).contiguous()
+    out = torch.empty((P, num_input_features), dtype=torch.float32, device=features.device)
+    h = nat.get_handle(features.device.index)
+    with torch.cuda.device(features.device):
+        nat.check(lib.lv_voxel_mean(h.ptr, features.data_ptr(), num.data_ptr(), P, T, C, num_input_features,
+                                    out.data_ptr(), nat.current_stream_ptr(features.device)))
+    return out
+
+
+@register_vfe
+class SimpleVoxel(nn.Module):
+    """voxel_encoder.py:207-225: per-voxel mean of the first num_input_features channels."""
+
+    def __init__(self, num_input_features=4, use_norm=True, num_filters=[32, 128], with_distance=False,
+                 voxel_size=(0.2, 0.2, 4), pc_range=(0, -40, -3, 70.4, 40, 1), name='VoxelFeatureExtractor'):
+        super().__init__()
+        self.name = name
+        self.num_input_features = num_input_features
+
+    def forward(self, features, num_voxels, coors):
+        return voxel_mean(features, num_voxels, self.num_input_features)
+
+
+@register_vfe
+class SimpleVoxelRadius(nn.Module):
+    """voxel_encoder.py:228-255: mean, then (|xy|, z, features...)."""
+
+    def __init__(self, num_input_features=4, use_norm=True, num_filters=(32, 128), with_distance=False,
+                 voxel_size=(0.2, 0.2, 4), pc_range=(0, -40, -3, 70.4, 40, 1), name='SimpleVoxelRadius'):
+        super().__init__()
+        self.num_input_features = num_input_features
+        self.name = name
+
+    def forward(self, features, num_voxels, coors):
+        mean = voxel_mean(features, num_voxels, self.num_input_features)
+        radius = torch.norm(mean[:, :2], p=2, dim=1, keepdim=True)
+        return torch.cat([radius, mean[:, 2:self.num_input_features]], dim=1)

@@ -1,0 +1,151 @@
+"""GPU parity: pillar decoration / scatter / voxel mean vs the reference's own
+outputs (tests/golden/ref_pillar_decorate.npz, ref_scatter.npz) and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from lyft3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6   # BASELINE.json north_star: pillar features within 1e-6 relative
+ATOL = 1e-5   # fp32 ulp of a +-50 m coordinate is 3.8e-6: differences x - mean inherit it
+
+
+@pytest.fixture(scope="module")
+def pp():
+    import torch
+    assert torch.cuda.is_available()
+    from lyft3d_b200 import pointpillars
+    return pointpillars
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_pillar_decorate.npz"))
+
+
+def _cuda(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+CLS = {"pfn": "PillarFeatureNet", "old": "PillarFeatureNetOld", "radius": "PillarFeatureNetRadius",
+       "radius_height": "PillarFeatureNetRadiusHeight"}
+
+
+@pytest.mark.parametrize("variant", list(CLS))
+@pytest.mark.parametrize("wd", [False, True])
+def test_decorate_vs_reference_outputs(pp, g, variant, wd):
+    cls = pp.get_vfe_class(CLS[variant])
+    net = cls(num_input_features=4, use_norm=True, num_filters=(64,), with_distance=wd,
+              voxel_size=synth.PILLAR_VOXEL_SIZE, pc_range=synth.PILLAR_RANGE).cuda()
+    out = net.decorate(_cuda(g["voxels"]), _cuda(g["num_points"]), _cuda(g["coors"])).cpu().numpy()
+    ref = g["dec_%s_%d" % (variant, int(wd))]
+    assert out.shape == ref.shape
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+    mask = np.arange(ref.shape[1])[None, :] < g["num_points"][:, None]
+    assert np.all(out[~mask] == 0)
+    # channels that are plain copies are bit-exact
+    if variant == "pfn":
+        assert np.array_equal(out[..., :4][mask], g["voxels"][mask])
+
+
+def test_full_pillar_feature_net_with_reference_weights(pp, g):
+    import torch
+    net = pp.PillarFeatureNet(num_input_features=4, use_norm=True, num_filters=(64,), with_distance=False,
+                              voxel_size=synth.PILLAR_VOXEL_SIZE, pc_range=synth.PILLAR_RANGE)
+    sd = {"pfn_layers.0.linear.weight": torch.from_numpy(g["pfn_weight"]),
+          "pfn_layers.0.norm.weight": torch.from_numpy(g["pfn_bn_gamma"]),
+          "pfn_layers.0.norm.bias": torch.from_numpy(g["pfn_bn_beta"]),
+          "pfn_layers.0.norm.running_mean": torch.from_numpy(g["pfn_bn_mean"]),
+          "pfn_layers.0.norm.running_var": torch.from_numpy(g["pfn_bn_var"]),
+          "pfn_layers.0.norm.num_batches_tracked": torch.tensor(0)}
+    net.load_state_dict(sd, strict=True)       # reference checkpoint keys load unchanged
+    net = net.cuda().eval()
+    with torch.no_grad():
+        out = net(_cuda(g["voxels"]), _cuda(g["num_points"]), _cuda(g["coors"])).cpu().numpy()
+    np.testing.assert_allclose(out, g["pfn_out"], rtol=1e-4, atol=1e-4)   # cuBLAS TF32-free fp32 GEMM order
+
+
+def test_decorate_large_vs_oracle(pp, cloud11):
+    from oracle import pillar_oracle as po, voxel_oracle as vo
+    v, c, n = vo.points_to_voxel(cloud11, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)
+    coors = po.merge_batch_coords([c])
+    net = pp.PillarFeatureNet(4, True, (64,), False, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE).cuda()
+    out = net.decorate(_cuda(v), _cuda(n), _cuda(coors)).cpu().numpy()
+    ref = po.decorate(v, n, coors, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE)
+    assert out.shape == (30000, 60, 9)
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+
+
+def test_decorate_generic_feature_count(pp):
+    from oracle import pillar_oracle as po
+    rng = np.random.default_rng(5)
+    P, T, C = 37, 11, 6
+    v = rng.normal(size=(P, T, C)).astype(np.float32) * 10
+    n = rng.integers(1, T + 1, size=P).astype(np.int32)
+    v[np.arange(T)[None, :] >= n[:, None]] = 0
+    coors = np.stack([np.zeros(P), np.zeros(P), rng.integers(0, 400, P), rng.integers(0, 400, P)], 1).astype(np.int32)
+    for variant in CLS:
+        out = pp.decorate_pillars(_cuda(v), _cuda(n), _cuda(coors), 0.25, 0.25, -49.875, -49.875, variant, True)
+        ref = po.decorate(v, n, coors, (0.25, 0.25, 20), synth.PILLAR_RANGE, variant, True)
+        np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+
+
+def test_scatter_vs_reference_output(pp, golden_dir):
+    s = np.load(os.path.join(golden_dir, "ref_scatter.npz"))
+    B, C, ny, nx = [int(v) for v in s["shape"]]
+    mod = pp.get_middle_class("PointPillarsScatter")(output_shape=[B, 1, ny, nx, C], num_input_features=C)
+    out = mod(_cuda(s["feats"]), _cuda(s["coords"]), B)
+    assert tuple(out.shape) == (B, C, ny, nx)
+    assert np.array_equal(out.cpu().numpy(), s["canvas"])       # pure copy: bit-exact
+    out2 = mod(_cuda(s["feats"]), _cuda(s["coords"]), B)         # workspace left clean
+    assert np.array_equal(out2.cpu().numpy(), s["canvas"])
+
+
+def test_scatter_full_size_and_backward(pp, fixture_nx4):
+    import torch
+    from oracle import pillar_oracle as po, voxel_oracle as vo
+    coords_list = []
+    for f in range(2):
+        _, c, _ = vo.points_to_voxel(synth.c5_frame(f), synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)
+        coords_list.append(c)
+    coords = po.merge_batch_coords(coords_list)
+    rng = np.random.default_rng(2)
+    feats = rng.normal(size=(coords.shape[0], 64)).astype(np.float32)
+    mod = pp.PointPillarsScatter(output_shape=[2, 1, 400, 400, 64], num_input_features=64)
+    ft = _cuda(feats).requires_grad_(True)
+    out = mod(ft, _cuda(coords), 2)
+    ref = po.scatter(feats, coords, 2, 400, 400)
+    assert np.array_equal(out.detach().cpu().numpy(), ref)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    co = torch.from_numpy(coords).long()
+    assert torch.equal(ft.grad.cpu(), w.cpu()[co[:, 0], :, co[:, 2], co[:, 3]])
+    # odd canvas (ncell % 4 != 0), C not multiple of 32
+    P = 50
+    cells = rng.permutation(3 * 7 * 9)[:P]
+    c2 = np.stack([cells // 63, np.zeros(P, np.int64), (cells % 63) // 9, cells % 9], 1).astype(np.int32)
+    f2 = rng.normal(size=(P, 5)).astype(np.float32)
+    o2 = pp.scatter_pillars(_cuda(f2), _cuda(c2), 3, 7, 9)
+    assert np.array_equal(o2.cpu().numpy(), po.scatter(f2, c2, 3, 7, 9))
+    # empty input
+    o3 = pp.scatter_pillars(_cuda(np.zeros((0, 64), np.float32)), _cuda(np.zeros((0, 4), np.int32)), 1, 400, 400)
+    assert float(o3.abs().sum()) == 0.0
+
+
+def test_simple_voxel(pp, g):
+    sv = pp.get_vfe_class("SimpleVoxel")(num_input_features=4)
+    out = sv(_cuda(g["voxels"]), _cuda(g["num_points"]), None).cpu().numpy()
+    np.testing.assert_allclose(out, g["simple_voxel"], rtol=RTOL, atol=ATOL)
+    svr = pp.get_vfe_class("SimpleVoxelRadius")(num_input_features=4)
+    out = svr(_cuda(g["voxels"]), _cuda(g["num_points"]), None).cpu().numpy()
+    np.testing.assert_allclose(out, g["simple_voxel_radius"], rtol=RTOL, atol=ATOL)
+
+
+def test_no_cpu_path(pp):
+    import torch
+    with pytest.raises(Exception):
+        pp.scatter_pillars(torch.zeros(4, 64), torch.zeros(4, 4, dtype=torch.int32), 1, 8, 8)
