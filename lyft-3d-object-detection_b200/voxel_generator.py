@@ -1,0 +1,175 @@
+"""Hard-voxelizer drop-ins (reference boundary: spconv.utils.VoxelGeneratorV2 as used by
+second/second/builder/voxel_builder.py:23-32 and second/second/data/preprocess.py:299-317).
+
+    VoxelGeneratorV2(voxel_size, point_cloud_range, max_num_points, max_voxels=20000,
+                     full_mean=False, block_filtering=False, block_factor=..., block_size=...,
+                     height_threshold=...)
+        .generate(points, max_voxels=None)       -> {"voxels","coordinates","num_points_per_voxel"[, ...]}
+        .generate_multi_gpu(points, max_voxels)  -> same, padded to max_voxels, + "voxel_num"
+        .voxel_size .point_cloud_range .grid_size .max_num_points_per_voxel
+    VoxelGenerator(...).generate(points, max_voxels) -> (voxels, coordinates, num_points_per_voxel)
+    points_to_voxel(points, voxel_size, coors_range, max_points=35, reverse_index=True, max_voxels=20000)
+        legacy tuple API (second/second/kittiviewer/viewer.py:389-396)
+
+The generator object is a plain picklable Python object holding only its
+configuration (it is captured in functools.partial for DataLoader workers and stored
+on the network); the native handle is created lazily per process.
+numpy in -> numpy out; CUDA tensor in -> CUDA tensors out (no host copies).
+``overflow`` selects what happens when max_voxels is hit: "continue" (spconv >= 1.1,
+default) or "break" (the in-tree rule, simplevis.py:48-49) - SURVEY.md F6.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native as nat
+
+
+def _is_cuda_tensor(x):
+    return hasattr(x, "is_cuda") and x.is_cuda
+
+
+def _make_config(voxel_size, coors_range, max_points, max_voxels, num_features, overflow, zero_tail):
+    cfg = nat.VoxelConfig()
+    cfg.voxel_size[:] = [float(v) for v in voxel_size]
+    cfg.coors_range[:] = [float(v) for v in coors_range]
+    cfg.max_points = int(max_points)
+    cfg.max_voxels = int(max_voxels)
+    cfg.num_features = int(num_features)
+    cfg.overflow_mode = nat.OVERFLOW_BREAK if overflow == "break" else nat.OVERFLOW_CONTINUE
+    cfg.zero_tail = int(bool(zero_tail))
+    return cfg
+
+
+def voxelize_frames(points, frame_offsets, voxel_size, coors_range, max_points, max_voxels,
+                    overflow="continue", zero_tail=True, handle=None):
+    """Batched voxelization of F independent clouds.
+
+    points (N_total, C) float32 rows (numpy or CUDA tensor); frame_offsets int64 (F+1).
+    Returns padded per-frame arrays: voxels (F,V,T,C), coordinates (F,V,3) zyx,
+    num_points_per_voxel (F,V), voxel_num (F).  With zero_tail=False rows at and
+    beyond voxel_num[f] are unspecified.
+    """
+    if overflow not in ("continue", "break"):
+        raise ValueError("overflow must be 'continue' or 'break'")
+    lib = nat.load()
+    offs = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+    F = offs.shape[0] - 1
+    V, T = int(max_voxels), int(max_points)
+    if _is_cuda_tensor(points):
+        import torch
+        if points.dim() != 2 or points.dtype != torch.float32:
+            raise ValueError("points must be a (N, C) float32 tensor")
+        pts = points.contiguous()
+        C = pts.shape[1]
+        dev = pts.device
+        cfg = _make_config(voxel_size, coors_range, T, V, C, overflow, zero_tail)
+        voxels = torch.empty((F, V, T, C), dtype=torch.float32, device=dev)
+        coords = torch.empty((F, V, 3), dtype=torch.int32, device=dev)
+        num = torch.empty((F, V), dtype=torch.int32, device=dev)
+        vnum = torch.empty((F,), dtype=torch.int32, device=dev)
+        h = handle or nat.get_handle(dev.index)
+        with torch.cuda.device(dev):
+            nat.check(lib.lv_voxelize(h.ptr, ctypes.byref(cfg), pts.data_ptr(), F, offs.ctypes.data,
+                                      voxels.data_ptr(), coords.data_ptr(), num.data_ptr(), vnum.data_ptr(),
+                                      nat.current_stream_ptr(dev)))
+        return voxels, coords, num, vnum
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    if pts.ndim != 2:
+        raise ValueError("points must be (N, C)")
+    C = pts.shape[1]
+    cfg = _make_config(voxel_size, coors_range, T, V, C, overflow, zero_tail)
+    alloc = np.zeros if not zero_tail else np.empty
+    voxels = alloc((F, V, T, C), dtype=np.float32)
+    coords = alloc((F, V, 3), dtype=np.int32)
+    num = alloc((F, V), dtype=np.int32)
+    vnum = np.zeros((F,), dtype=np.int32)
+    h = handle or nat.get_handle()
+    nat.check(lib.lv_voxelize_host(h.ptr, ctypes.byref(cfg), pts.ctypes.data, F, offs.ctypes.data,
+                                   voxels.ctypes.data, coords.ctypes.data, num.ctypes.data, vnum.ctypes.data))
+    return voxels, coords, num, vnum
+
+
+class VoxelGeneratorV2:
+    """spconv.utils.VoxelGeneratorV2-compatible generator (see module docstring)."""
+
+    def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels=20000, full_mean=False,
+                 block_filtering=False, block_factor=8, block_size=3, height_threshold=0.1,
+                 height_high_threshold=2.0, overflow="continue"):
+        assert full_mean is False, "full_mean is not supported (spconv asserts the same)"
+        if block_filtering:
+            raise NotImplementedError("block_filtering voxelization is out of the first scope (SURVEY.md 8f n4)")
+        if overflow not in ("continue", "break"):
+            raise ValueError("overflow must be 'continue' or 'break'")
+        point_cloud_range = np.array(point_cloud_range, dtype=np.float32)
+        voxel_size = np.array(voxel_size, dtype=np.float32)
+        grid_size = (point_cloud_range[3:] - point_cloud_range[:3]) / voxel_size
+        grid_size = np.round(grid_size).astype(np.int64)
+        self._voxel_size = voxel_size
+        self._point_cloud_range = point_cloud_range
+        self._max_num_points = int(max_num_points)
+        self._max_voxels = int(max_voxels)
+        self._grid_size = grid_size
+        self._full_mean = full_mean
+        self._overflow = overflow
+
+    # -- the V2 dict API (preprocess.py:305-317, inference.py:68-69)
+    def _run(self, points, max_voxels, padded):
+        mv = self._max_voxels if max_voxels is None else int(max_voxels)
+        n = points.shape[0]
+        voxels, coords, num, vnum = voxelize_frames(
+            points, np.array([0, n], dtype=np.int64), self._voxel_size, self._point_cloud_range,
+            self._max_num_points, mv, overflow=self._overflow, zero_tail=padded)
+        k = int(vnum[0])
+        return voxels[0], coords[0], num[0], k
+
+    def generate(self, points, max_voxels=None):
+        voxels, coords, num, k = self._run(points, max_voxels, padded=False)
+        return {"voxels": voxels[:k], "coordinates": coords[:k], "num_points_per_voxel": num[:k],
+                "voxel_num": k}
+
+    def generate_multi_gpu(self, points, max_voxels=None):
+        voxels, coords, num, k = self._run(points, max_voxels, padded=True)
+        return {"voxels": voxels, "coordinates": coords, "num_points_per_voxel": num, "voxel_num": k}
+
+    @property
+    def voxel_size(self):
+        return self._voxel_size
+
+    @property
+    def max_num_points_per_voxel(self):
+        return self._max_num_points
+
+    @property
+    def point_cloud_range(self):
+        return self._point_cloud_range
+
+    @property
+    def grid_size(self):
+        return self._grid_size
+
+
+class VoxelGenerator(VoxelGeneratorV2):
+    """V1-style generator: generate() returns the tuple (voxels, coordinates, num_points_per_voxel)."""
+
+    def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels=20000, overflow="break"):
+        super().__init__(voxel_size, point_cloud_range, max_num_points, max_voxels, overflow=overflow)
+
+    def generate(self, points, max_voxels=None):
+        res = super().generate(points, max_voxels)
+        return res["voxels"], res["coordinates"], res["num_points_per_voxel"]
+
+
+def points_to_voxel(points, voxel_size, coors_range, max_points=35, reverse_index=True, max_voxels=20000,
+                    overflow="break"):
+    """Legacy tuple API (numba point_cloud_ops.points_to_voxel; call sites
+    second/second/kittiviewer/viewer.py:389-396,509-516,573-579).  reverse_index=True
+    returns zyx coordinates (the only form the reference uses); False returns xyz."""
+    n = points.shape[0]
+    voxels, coords, num, vnum = voxelize_frames(points, np.array([0, n], dtype=np.int64), voxel_size, coors_range,
+                                                max_points, max_voxels, overflow=overflow, zero_tail=False)
+    k = int(vnum[0])
+    co = coords[0][:k]
+    if not reverse_index:
+        co = co.flip(-1) if _is_cuda_tensor(co) else co[:, ::-1].copy()
+    return voxels[0][:k], co, num[0][:k]

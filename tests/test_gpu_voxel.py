@@ -1,0 +1,187 @@
+"""GPU parity: hard voxelizer (C-ABI, sm_100a kernels) vs the CPU oracle - all four
+outputs bit-exact including voxel order, in both overflow modes."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from lyft3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+@pytest.fixture(scope="module")
+def vg():
+    import torch
+    assert torch.cuda.is_available()
+    from lyft3d_b200 import voxel_generator
+    return voxel_generator
+
+
+@pytest.fixture(scope="module")
+def vo():
+    from oracle import voxel_oracle
+    return voxel_oracle
+
+
+def check_equal(res, ref):
+    v, c, n = ref
+    assert res["voxels"].shape == v.shape and res["voxels"].dtype == np.float32
+    assert res["coordinates"].dtype == np.int32 and res["num_points_per_voxel"].dtype == np.int32
+    assert np.array_equal(res["coordinates"], c)
+    assert np.array_equal(res["num_points_per_voxel"], n)
+    assert np.array_equal(res["voxels"].view(np.uint32), v.view(np.uint32))   # bit-exact incl. -0.0
+
+
+@pytest.mark.parametrize("mode", ["continue", "break"])
+def test_c3_single_sweep_pillars(vg, vo, fixture_nx4, mode):
+    gen = vg.VoxelGeneratorV2(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, synth.PILLAR_MAX_POINTS,
+                              max_voxels=synth.PILLAR_MAX_VOXELS, overflow=mode)
+    res = gen.generate(fixture_nx4, synth.PILLAR_MAX_VOXELS)
+    ref = vo.points_to_voxel(fixture_nx4, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000, overflow=mode)
+    assert res["voxel_num"] == 8569
+    check_equal(res, ref)
+    res2 = gen.generate(fixture_nx4, synth.PILLAR_MAX_VOXELS)   # dense map was reset
+    check_equal(res2, ref)
+
+
+@pytest.mark.parametrize("mode", ["continue", "break"])
+@pytest.mark.parametrize("case", ["c2_11", "c2_20", "c3_11", "c3_20", "c3_20_train25000"])
+def test_frozen_configs(vg, vo, golden_dir, cloud11, cloud20, case, mode):
+    with open(os.path.join(golden_dir, "voxel_oracle_hashes.json")) as f:
+        fz = json.load(f)["%s_%s" % (case, mode)]
+    pts = cloud11 if case.endswith("_11") else cloud20
+    if case.startswith("c2"):
+        vs, rg, T, mv = synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, 60000
+    else:
+        vs, rg, T, mv = synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, (25000 if "25000" in case else 30000)
+    gen = vg.VoxelGeneratorV2(vs, rg, T, max_voxels=mv, overflow=mode)
+    res = gen.generate(pts, mv)
+    assert res["voxel_num"] == fz["voxel_num"]
+    assert int(res["num_points_per_voxel"].sum()) == fz["stored_points"]
+    assert sha16(res["coordinates"]) == fz["sha_coords"]
+    assert sha16(res["num_points_per_voxel"]) == fz["sha_num"]
+    assert sha16(res["voxels"]) == fz["sha_voxels"]
+    check_equal(res, vo.points_to_voxel(pts, vs, rg, T, mv, overflow=mode))
+
+
+def test_generator_properties_and_padded_api(vg, vo, cloud11):
+    gen = vg.VoxelGeneratorV2(list(synth.SECOND_VOXEL_SIZE), list(synth.SECOND_RANGE), 5, max_voxels=20000)
+    assert gen.grid_size.tolist() == [1056, 1280, 40]
+    assert gen.voxel_size.dtype == np.float32 and gen.point_cloud_range.dtype == np.float32
+    assert gen.point_cloud_range[[0, 1, 3, 4]].tolist() == [0.0, -32.0, pytest.approx(52.8), 32.0]
+    assert gen.max_num_points_per_voxel == 5
+    import pickle
+    gen = pickle.loads(pickle.dumps(gen))                       # plain picklable object
+    res = gen.generate_multi_gpu(cloud11, 70000)                # cap not reached -> padding rows
+    v, c, n, k = vo.VoxelOracle(synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, 70000).generate(
+        cloud11, padded=True)
+    assert res["voxel_num"] == k
+    assert res["voxels"].shape == (70000, 5, 4)
+    assert np.array_equal(res["voxels"], v) and np.array_equal(res["coordinates"], c)
+    assert np.array_equal(res["num_points_per_voxel"], n)
+    # default max_voxels of the constructor is used when generate() gets none
+    r2 = gen.generate(cloud11)
+    assert r2["voxels"].shape[0] == 20000
+
+
+def test_legacy_tuple_apis(vg, vo, fixture_nx4):
+    ref = vo.points_to_voxel(fixture_nx4, (0.2, 0.2, 0.4), (0, -40, -3, 70.4, 40, 1), 35, 20000, overflow="break")
+    v, c, n = vg.points_to_voxel(fixture_nx4, (0.2, 0.2, 0.4), (0, -40, -3, 70.4, 40, 1), 35, True, 20000)
+    assert np.array_equal(v, ref[0]) and np.array_equal(c, ref[1]) and np.array_equal(n, ref[2])
+    v, c2, n = vg.points_to_voxel(fixture_nx4, (0.2, 0.2, 0.4), (0, -40, -3, 70.4, 40, 1), 35, False, 20000)
+    assert np.array_equal(c2, ref[1][:, ::-1])
+    g1 = vg.VoxelGenerator((0.2, 0.2, 0.4), (0, -40, -3, 70.4, 40, 1), 35, 20000)
+    t = g1.generate(fixture_nx4, 20000)
+    assert isinstance(t, tuple) and np.array_equal(t[0], ref[0])
+
+
+def test_cuda_tensor_in_out(vg, vo, fixture_nx4):
+    import torch
+    gen = vg.VoxelGeneratorV2(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, max_voxels=30000)
+    res = gen.generate(torch.from_numpy(fixture_nx4).cuda(), 30000)
+    assert res["voxels"].is_cuda
+    ref = vo.points_to_voxel(fixture_nx4, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)
+    assert np.array_equal(res["voxels"].cpu().numpy(), ref[0])
+    assert np.array_equal(res["coordinates"].cpu().numpy(), ref[1])
+    assert np.array_equal(res["num_points_per_voxel"].cpu().numpy(), ref[2])
+
+
+@pytest.mark.parametrize("mode", ["continue", "break"])
+def test_batched_frames_ragged(vg, vo, mode):
+    """C5-style batch: ragged frames incl. an empty one and one with every point out of range;
+    small max_voxels so that the cap and both overflow rules are exercised per frame."""
+    frames = [synth.c5_frame(0), synth.c5_frame(1)[:30011], np.zeros((0, 4), np.float32),
+              synth.c5_frame(2)[:2049], np.full((100, 4), 1e6, np.float32), synth.c5_frame(3)[:1]]
+    frames += [synth.c5_frame(10 + f)[: 4000 + 37 * f] for f in range(20)]
+    rows = np.concatenate(frames)
+    offs = np.zeros(len(frames) + 1, np.int64)
+    offs[1:] = np.cumsum([f.shape[0] for f in frames])
+    T, V = 9, 2500
+    voxels, coords, num, vnum = vg.voxelize_frames(rows, offs, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, T, V,
+                                                   overflow=mode, zero_tail=True)
+    orc = vo.VoxelOracle(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, T, V)
+    for f, fr in enumerate(frames):
+        v, c, n, k = orc.generate(fr, overflow=mode, padded=True)
+        assert vnum[f] == k, f
+        assert np.array_equal(coords[f], c) and np.array_equal(num[f], n), f
+        assert np.array_equal(voxels[f].view(np.uint32), v.view(np.uint32)), f
+
+
+def test_generic_feature_count_and_three_passes(vg, vo, cloud11):
+    # C = 5 features (non-float4 path) and max_voxels > 2^18 -> three radix passes
+    rng = np.random.default_rng(9)
+    pts5 = np.concatenate([cloud11[:300000], rng.normal(size=(300000, 1)).astype(np.float32)], axis=1)
+    vs, rg, T, mv = (0.05, 0.05, 0.1), synth.SECOND_RANGE, 3, 300000
+    gen = vg.VoxelGeneratorV2(vs, rg, T, max_voxels=mv)
+    res = gen.generate(pts5, mv)
+    check_equal(res, vo.points_to_voxel(pts5, vs, rg, T, mv))
+    # C = 3
+    pts3 = np.ascontiguousarray(cloud11[:100000, :3])
+    gen = vg.VoxelGeneratorV2(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 4, max_voxels=5000)
+    check_equal(gen.generate(pts3, 5000), vo.points_to_voxel(pts3, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 4, 5000))
+
+
+def test_edges_and_errors(vg, vo):
+    gen = vg.VoxelGeneratorV2(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 5, max_voxels=100)
+    r = gen.generate(np.zeros((0, 4), np.float32), 100)
+    assert r["voxels"].shape == (0, 5, 4) and r["coordinates"].shape == (0, 3)
+    pts = np.array([[50.0, 0, 0, 0], [49.999, 0, 0, 0], [-50.0, 0, 0, 0], [-50.001, 0, 0, 0],
+                    [0, 0, 10.0, 0], [0, 0, -10.0, 0], [np.nan, 0, 0, 0], [0, np.inf, 0, 0]], np.float32)
+    r = gen.generate(pts, 100)
+    assert r["coordinates"].tolist() == [[0, 200, 399], [0, 200, 0], [0, 200, 200]]
+    # one voxel, more points than max_points: the FIRST T points in index order are kept
+    same = np.tile(np.array([[1.01, 1.01, 0.0, 0.0]], np.float32), (1000, 1))
+    same[:, 3] = np.arange(1000)
+    r = gen.generate(same, 100)
+    assert r["num_points_per_voxel"].tolist() == [5] and r["voxels"][0, :, 3].tolist() == [0, 1, 2, 3, 4]
+    with pytest.raises(Exception):
+        vg.VoxelGeneratorV2(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 5, block_filtering=True)
+    with pytest.raises(Exception):
+        vg.VoxelGeneratorV2((0.001, 0.001, 0.001), synth.PILLAR_RANGE, 5).generate(pts, 10)   # grid > 2^28 cells
+
+
+def test_order_properties_at_full_size(vg, cloud11):
+    """Size-independent properties at full size: coordinates unique, every stored point lies in
+    its voxel, slots hold increasing point indices (channel 3 carries the index)."""
+    pts = cloud11.copy()
+    pts[:, 3] = np.arange(pts.shape[0], dtype=np.float32)     # exact below 2^24
+    gen = vg.VoxelGeneratorV2(synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, max_voxels=60000)
+    r = gen.generate(pts, 60000)
+    v, c, n = r["voxels"], r["coordinates"], r["num_points_per_voxel"]
+    assert len(np.unique(c, axis=0)) == c.shape[0] == 60000
+    mask = np.arange(5)[None, :] < n[:, None]
+    idx = np.where(mask, v[..., 3], np.inf)
+    d = np.diff(idx, axis=1)
+    assert np.all(d[mask[:, 1:]] > 0)                          # slots in point order
+    assert np.all(np.diff(idx[:, 0]) > 0)                      # voxel order == order of first appearance
+    lo = np.asarray(synth.SECOND_RANGE[:3], np.float32)
+    vs = np.asarray(synth.SECOND_VOXEL_SIZE, np.float32)
+    cc = np.floor((v[..., :3] - lo) / vs).astype(np.int32)[..., ::-1]
+    assert np.all((cc == c[:, None, :])[mask])
