@@ -174,6 +174,20 @@ int lv_voxelize(lv_handle* h, const lv_voxel_config* cfg, const float* d_points,
                 int32_t* d_coords, int32_t* d_num_points, int32_t* d_voxel_num,
                 lv_stream stream);
 
+/* Same voxelization, batch-assembled on the device the way merge_second_batch does
+ * on the host (second/second/data/preprocess.py:21-55): the voxels of all frames
+ * back to back, coordinates with the batch index prepended.
+ *   d_voxels        float32 (capacity_rows, T, C)
+ *   d_coords4       int32   (capacity_rows, 4)   [batch, z, y, x]   (16-byte aligned)
+ *   d_num_points    int32   (capacity_rows)
+ *   d_voxel_num     int32   (n_frames)
+ *   d_voxel_offsets int64   (n_frames + 1)  first row of every frame; [n_frames] = total rows.
+ * Rows beyond capacity_rows are dropped: the caller checks d_voxel_offsets[n_frames]. */
+int lv_voxelize_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points,
+                       int32_t n_frames, const int64_t* h_frame_offsets, int64_t capacity_rows,
+                       float* d_voxels, int32_t* d_coords4, int32_t* d_num_points,
+                       int32_t* d_voxel_num, int64_t* d_voxel_offsets, lv_stream stream);
+
 int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const float* h_points,
                      int32_t n_frames, const int64_t* h_frame_offsets, float* h_voxels,
                      int32_t* h_coords, int32_t* h_num_points, int32_t* h_voxel_num);

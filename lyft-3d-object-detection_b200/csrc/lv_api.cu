@@ -113,15 +113,7 @@ int lv_destroy(lv_handle* h) {
   if (!h) return LV_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  lv_buffer* bufs[] = {&h->bev_counts, &h->bev_seg_offsets.dev, &h->bev_seg_frame.dev, &h->bev_seg_tm.dev,
-                       &h->bev_stage_points, &h->bev_stage_out[0], &h->bev_stage_out[1], &h->bev_stage_out[2],
-                       &h->bev_stage_out[3], &h->bev_stage_out[4], &h->bev_stage_map,
-                       &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1],
-                       &h->vox_vals[0], &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state,
-                       &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_stage_points,
-                       &h->vox_stage_out[0], &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3],
-                       &h->pil_map};
-  for (lv_buffer* b : bufs) b->release();
+  for (lv_buffer* b : lv_all_buffers(h)) b->release();
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return LV_OK;
@@ -129,16 +121,8 @@ int lv_destroy(lv_handle* h) {
 
 int64_t lv_workspace_bytes(lv_handle* h) {
   if (!h) return 0;
-  lv_buffer* bufs[] = {&h->bev_counts, &h->bev_seg_offsets.dev, &h->bev_seg_frame.dev, &h->bev_seg_tm.dev,
-                       &h->bev_stage_points, &h->bev_stage_out[0], &h->bev_stage_out[1], &h->bev_stage_out[2],
-                       &h->bev_stage_out[3], &h->bev_stage_out[4], &h->bev_stage_map,
-                       &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1],
-                       &h->vox_vals[0], &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state,
-                       &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_stage_points,
-                       &h->vox_stage_out[0], &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3],
-                       &h->pil_map};
   int64_t total = 0;
-  for (lv_buffer* b : bufs) total += (int64_t)b->cap;
+  for (lv_buffer* b : lv_all_buffers(h)) total += (int64_t)b->cap;
   return total;
 }
 

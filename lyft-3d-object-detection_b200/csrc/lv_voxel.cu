@@ -72,6 +72,10 @@ struct VoxParams {
   int32_t* seg_end;
   // outputs
   float* voxels; int32_t* coords; int32_t* num_points; int32_t* voxel_num;
+  int64_t* row_base;           // [F+1] first output row of every frame (padded: f*V; concat: prefix of voxel_num)
+  int concat;                  // 1: frames back to back, coords carry the batch index (coord_cols == 4)
+  int coord_cols;              // 3 (z,y,x) or 4 (b,z,y,x)
+  int64_t capacity;            // output rows available
 };
 
 struct ChunkLoc {
@@ -229,6 +233,28 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scan_chunks_kernel(VoxParams p)
     p.frame_total[fl] = total;
     p.frame_cut[fl] = 0x7fffffff;
     p.voxel_num[f] = total < p.V ? total : p.V;
+    if (!p.concat) {
+      p.row_base[f] = (int64_t)f * p.V;
+      if (f + 1 == p.f1) p.row_base[f + 1] = (int64_t)(f + 1) * p.V;
+    }
+  }
+}
+
+// concat layout (merge_second_batch, second/second/data/preprocess.py:28-50): row_base = prefix of voxel_num
+__global__ void vx_row_base_kernel(VoxParams p) {
+  const int lane = threadIdx.x;
+  int64_t carry = p.row_base[p.f0];
+  for (int b = p.f0; b < p.f1; b += 32) {
+    const int f = b + lane;
+    int v = f < p.f1 ? p.voxel_num[f] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (f < p.f1) p.row_base[f + 1] = carry + inc;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
   }
 }
 
@@ -271,6 +297,7 @@ __global__ void __launch_bounds__(VX_THREADS) vx_assign_kernel(VoxParams p) {
   int rank = p.chunk_cnt[blockIdx.x] + woff + inc - s;
   if (flags == 0) return;
   const int gx = p.grid[0], gy = p.grid[1];
+  const int64_t row0 = p.row_base[L.f];
 #pragma unroll
   for (int k = 0; k < VX_ITEMS; ++k) {
     if (!(flags & (1u << k))) continue;
@@ -280,8 +307,15 @@ __global__ void __launch_bounds__(VX_THREADS) vx_assign_kernel(VoxParams p) {
     p.cell[L.start + li - p.pt_lo] = c | VX_CREATOR_BIT;
     if (rank < p.V) {
       const int cx = c % gx, cy = (c / gx) % gy, cz = c / (gx * gy);
-      int32_t* co = p.coords + ((int64_t)L.f * p.V + rank) * 3;
-      co[0] = cz; co[1] = cy; co[2] = cx;  // reversed (z,y,x), simplevis.py:42
+      const int64_t row = row0 + rank;
+      if (row < p.capacity) {
+        if (p.coord_cols == 4) {  // batch index first (preprocess.py:44-50)
+          *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(L.f, cz, cy, cx);
+        } else {
+          int32_t* co = p.coords + row * 3;
+          co[0] = cz; co[1] = cy; co[2] = cx;  // reversed (z,y,x), simplevis.py:42
+        }
+      }
     } else if (rank == p.V && p.overflow == LV_OVERFLOW_BREAK) {
       p.frame_cut[L.fl] = li;  // simplevis.py:48-49: the loop stops here
     }
@@ -468,8 +502,9 @@ __global__ void __launch_bounds__(VX_THREADS) vx_gather_kernel(VoxParams p, cons
   const int v = (int)(((int64_t)blockIdx.x * VX_THREADS + threadIdx.x) / LPV);
   if (v >= p.V) return;
   const int vnum = p.voxel_num[f];
-  if (v >= vnum && !p.zero_tail) return;
-  const int64_t row = (int64_t)f * p.V + v;
+  if (v >= vnum && (!p.zero_tail || p.concat)) return;
+  const int64_t row = p.row_base[f] + v;
+  if (row >= p.capacity) return;
   float* out = p.voxels + row * p.T * p.C;
   int n = 0;
   int s = 0;
@@ -481,8 +516,8 @@ __global__ void __launch_bounds__(VX_THREADS) vx_gather_kernel(VoxParams p, cons
   if (sub == 0) {
     p.num_points[row] = n;
     if (v >= vnum) {
-      int32_t* co = p.coords + row * 3;
-      co[0] = 0; co[1] = 0; co[2] = 0;
+      int32_t* co = p.coords + row * p.coord_cols;
+      for (int j = 0; j < p.coord_cols; ++j) co[j] = 0;
     }
   }
   const int64_t fstart = __ldg(p.frame_off + f);
@@ -536,9 +571,9 @@ static int vx_bits_for(int v) {  // bits needed for ids in [0, v)
   return b;
 }
 
-extern "C" int lv_voxelize(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
-                           const int64_t* h_frame_offsets, float* d_voxels, int32_t* d_coords, int32_t* d_num_points,
-                           int32_t* d_voxel_num, lv_stream stream_) {
+static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
+                  const int64_t* h_frame_offsets, float* d_voxels, int32_t* d_coords, int32_t* d_num_points,
+                  int32_t* d_voxel_num, int concat, int64_t capacity, int64_t* d_row_base, lv_stream stream_) {
   LV_REQUIRE(h != nullptr, "lv_voxelize: null handle");
   LV_REQUIRE(cfg && h_frame_offsets, "lv_voxelize: null config / frame offsets");
   LV_REQUIRE(n_frames >= 0, "lv_voxelize: negative frame count");
@@ -600,6 +635,18 @@ extern "C" int lv_voxelize(lv_handle* h, const lv_voxel_config* cfg, const float
   }
   p.G = G; p.T = T; p.V = V; p.overflow = cfg->overflow_mode; p.zero_tail = cfg->zero_tail;
   p.voxels = d_voxels; p.coords = d_coords; p.num_points = d_num_points; p.voxel_num = d_voxel_num;
+  p.concat = concat;
+  p.coord_cols = concat ? 4 : 3;
+  p.capacity = concat ? capacity : (int64_t)n_frames * V;
+  if (!d_row_base) {
+    LV_CHECK(h->vox_row_base.ensure((size_t)(n_frames + 1) * sizeof(int64_t), stream));
+    d_row_base = h->vox_row_base.as<int64_t>();
+  }
+  p.row_base = d_row_base;
+  if (concat) {
+    LV_REQUIRE((reinterpret_cast<uintptr_t>(d_coords) & 15) == 0, "lv_voxelize_concat: coords must be 16-byte aligned");
+    LV_CHECK_CUDA(cudaMemsetAsync(d_row_base, 0, sizeof(int64_t), stream));
+  }
   const bool c4 = (C == 4) && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0;
   const bool out4 = c4 && (reinterpret_cast<uintptr_t>(d_voxels) & 15) == 0;
 
@@ -641,6 +688,10 @@ extern "C" int lv_voxelize(lv_handle* h, const lv_voxel_config* cfg, const float
     }
     vx_scan_chunks_kernel<<<nf, VX_THREADS, 0, stream>>>(p);
     LV_LAUNCH_CHECK(h);
+    if (concat) {
+      vx_row_base_kernel<<<1, 32, 0, stream>>>(p);
+      LV_LAUNCH_CHECK(h);
+    }
     const uint32_t* sorted_keys = p.keyA;
     const int32_t* sorted_vals = p.valA;
     if (nchunks > 0) {
@@ -687,6 +738,23 @@ extern "C" int lv_voxelize(lv_handle* h, const lv_voxel_config* cfg, const float
     f0 = f1;
   }
   return LV_OK;
+}
+
+extern "C" int lv_voxelize(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
+                           const int64_t* h_frame_offsets, float* d_voxels, int32_t* d_coords, int32_t* d_num_points,
+                           int32_t* d_voxel_num, lv_stream stream) {
+  return vx_run(h, cfg, d_points, n_frames, h_frame_offsets, d_voxels, d_coords, d_num_points, d_voxel_num, 0, 0,
+                nullptr, stream);
+}
+
+extern "C" int lv_voxelize_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
+                                  const int64_t* h_frame_offsets, int64_t capacity_rows, float* d_voxels,
+                                  int32_t* d_coords4, int32_t* d_num_points, int32_t* d_voxel_num,
+                                  int64_t* d_voxel_offsets, lv_stream stream) {
+  LV_REQUIRE(capacity_rows >= 0, "lv_voxelize_concat: negative capacity");
+  LV_REQUIRE(n_frames == 0 || d_voxel_offsets, "lv_voxelize_concat: null voxel_offsets");
+  return vx_run(h, cfg, d_points, n_frames, h_frame_offsets, d_voxels, d_coords4, d_num_points, d_voxel_num, 1,
+                capacity_rows, d_voxel_offsets, stream);
 }
 
 extern "C" int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const float* h_points, int32_t n_frames,
