@@ -43,6 +43,7 @@ def workload_cfg():
 def config_json(frames_per_step, n_gpus, extra=None):
     c = {"workload": "C5 throughput sweep: synthetic 53,146-point Lyft sweeps, BEV 336x336x3 (norm f32 + u8) "
                      "+ pillar path (voxelize 0.25 m/T=60/V=30000 -> decorate -> scatter 64x400x400)",
+         "pillar_path": "fused voxelize+decorate" if not (extra or {}).get("unfused") else "separate voxelize, decorate",
          "frames_per_step_per_gpu": frames_per_step, "points_per_frame": 53146,
          "parallelism": "frames sharded f mod G, dp%d, no collective" % n_gpus,
          "l2": "inputs (pool of distinct frames) and outputs per step exceed the 126 MB L2"}
@@ -175,6 +176,7 @@ def main():
     ap.add_argument("--pool-frames", type=int, default=256)
     ap.add_argument("--cpu-frames", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="voxelize and decorate as separate stages")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -212,29 +214,39 @@ def main():
         b = s % n_batches
         return pool_pts[b * F * n:(b + 1) * F * n]
 
-    stages = ["bev", "voxelize", "decorate", "scatter"]
+    fused = not args.unfused
+    stages = ["bev", "pillarize", "scatter"] if fused else ["bev", "voxelize", "decorate", "scatter"]
 
     def run_steps(k, record):
         evs = []
         rows_seen = []
         for s in range(k):
             pts = batch(s)
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record else None
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] if record else None
+            i = 0
             if record:
-                e[0].record()
+                e[i].record()
             eng.bev(pts)
+            i += 1
             if record:
-                e[1].record()
-            eng.voxelize(pts)
-            rows = eng.read_total_rows()
+                e[i].record()
+            if fused:
+                eng.pillarize(pts)
+                rows = eng.read_total_rows()
+            else:
+                eng.voxelize(pts)
+                rows = eng.read_total_rows()
+                i += 1
+                if record:
+                    e[i].record()
+                eng.decorate(rows)
+            i += 1
             if record:
-                e[2].record()
-            eng.decorate(rows)
-            if record:
-                e[3].record()
+                e[i].record()
             eng.scatter(rows)
+            i += 1
             if record:
-                e[4].record()
+                e[i].record()
                 evs.append(e)
             rows_seen.append(rows)
         return evs, rows_seen
@@ -274,7 +286,7 @@ def main():
 
     def e2e_step():
         dev_pts.copy_(host_pts, non_blocking=True)
-        eng.step(dev_pts)
+        eng.step(dev_pts, fused=fused)
         host_u8.copy_(eng.bev_u8, non_blocking=True)
         host_vnum.copy_(eng.voxel_num, non_blocking=True)
         torch.cuda.synchronize()
@@ -312,6 +324,7 @@ def main():
             "bev": F * (16 * n + 4 * cells + 1 * cells),
             "voxelize": F * 16 * n + mean_rows * (T * C * 4 + 16 + 4),
             "decorate": mean_rows * (T * C * 4 + 20 + T * (C + 5) * 4),
+            "pillarize": F * 16 * n + mean_rows * (T * (C + 5) * 4 + 16 + 4),
             "scatter": mean_rows * (eng.channels * 4 + 16) + F * eng.channels * eng.ny * eng.nx * 4,
         }
         stage_info = {}
@@ -322,16 +335,17 @@ def main():
                               "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
         dom = max(stages, key=lambda s: stage_ms[s])
         kernel_names = {"bev": "bev_hist_kernel+bev_finalize_flat4_kernel", "voxelize": "vx_* (13 kernels)",
-                        "decorate": "pillar_decorate_kernel", "scatter": "pillar_canvas_kernel"}
+                        "decorate": "pillar_decorate_fast_kernel", "scatter": "pillar_canvas_kernel",
+                        "pillarize": "vx_* (12 kernels) + vx_gather_decorate_kernel"}
         roof = {"bound": "hbm", "kernel": kernel_names[dom], "stage": dom,
                 "achieved": stage_info[dom]["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": round(stage_info[dom]["GBps"] / peak, 4), "traffic": None,
-                "whole_step_frac": round(sum(alg.values()) / (ms_total / args.steps * 1e-3) / 1e9 / peak, 4)}
+                "whole_step_frac": round(sum(alg[st] for st in stages) / (ms_total / args.steps * 1e-3) / 1e9 / peak, 4)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 points, f64 BEV affine, u32 counts",
                 "data": "synthetic",
-                "config": config_json(F, world, {"mean_pillars_per_frame": round(mean_rows / F, 1)}),
+                "config": config_json(F, world, {"mean_pillars_per_frame": round(mean_rows / F, 1), "unfused": not fused}),
                 "roofline": roof, "stages": stage_info, "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * n * 16,
                         "d2h_bytes_per_step": F * cells + F * 4,

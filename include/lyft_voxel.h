@@ -218,6 +218,19 @@ int lv_pillar_decorate(lv_handle* h, const float* d_voxels, const int32_t* d_num
                        float y_offset, int32_t variant, int32_t with_distance, float* d_out,
                        lv_stream stream);
 
+/* Voxelization fused with the decoration (north_star: "pillar decoration is fused into
+ * the gather"): lv_voxelize_concat followed by lv_pillar_decorate, without ever writing
+ * the (P,T,C) voxel tensor.  d_decorated is (capacity_rows, T, C_out) float32; the other
+ * outputs are those of lv_voxelize_concat.  Needs num_features == 4 and max_points <= 64.
+ * Replaces second/second/data/preprocess.py:299-317 + :21-55 and
+ * second/second/pytorch/models/pointpillars.py:203-231 in one call. */
+int lv_pillarize_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points,
+                        int32_t n_frames, const int64_t* h_frame_offsets, int64_t capacity_rows,
+                        float vx, float vy, float x_offset, float y_offset, int32_t variant,
+                        int32_t with_distance, float* d_decorated, int32_t* d_coords4,
+                        int32_t* d_num_points, int32_t* d_voxel_num, int64_t* d_voxel_offsets,
+                        lv_stream stream);
+
 /* lv_pillar_scatter replaces PointPillarsScatter.forward
  * (second/second/pytorch/models/pointpillars.py:444-476):
  * canvas[b, c, y, x] = feats[p, c] for the pillar p with coords[p] = (b, ., y, x),

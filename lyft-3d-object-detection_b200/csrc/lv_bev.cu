@@ -113,26 +113,40 @@ __device__ __forceinline__ void bev_cell(unsigned c, float max_intensity, float&
   q = (uint8_t)rintf(__fmul_rn(nrm, 255.0f));                      // np.round(bev*255).astype(uint8), :213
 }
 
-// flat path: 4 consecutive cells per thread (cells % 4 == 0)
+// flat path: 4 consecutive cells per thread-item (cells % 4 == 0).  grid = (x, frames in
+// flight); 4 independent 128-bit loads are issued before any store (memory-level parallelism).
+#define BEV_FIN_UNROLL 4
 __global__ void __launch_bounds__(256) bev_finalize_flat4_kernel(unsigned* counts, BevOut o) {
-  const int64_t quads_per_frame = o.cells / 4;
-  const int64_t total = quads_per_frame * o.n_frames;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    uint4* cp = reinterpret_cast<uint4*>(counts) + q;
-    const uint4 c = *cp;
-    *cp = make_uint4(0, 0, 0, 0);
-    const int64_t f = q / quads_per_frame;
-    const int64_t out_q = (o.frame_base + f) * quads_per_frame + (q - f * quads_per_frame);
-    float4 r, n;
-    uchar4 b;
-    bev_cell(c.x, o.max_intensity, r.x, n.x, b.x);
-    bev_cell(c.y, o.max_intensity, r.y, n.y, b.y);
-    bev_cell(c.z, o.max_intensity, r.z, n.z, b.z);
-    bev_cell(c.w, o.max_intensity, r.w, n.w, b.w);
-    if (o.raw) lv_st_stream_f4(reinterpret_cast<float4*>(o.raw) + out_q, r);
-    if (o.norm) lv_st_stream_f4(reinterpret_cast<float4*>(o.norm) + out_q, n);
-    if (o.u8) reinterpret_cast<uchar4*>(o.u8)[out_q] = b;
+  const unsigned quads = o.cells / 4;
+  const unsigned f = blockIdx.y;
+  uint4* cp = reinterpret_cast<uint4*>(counts) + (size_t)f * quads;
+  const size_t out0 = (size_t)(o.frame_base + f) * quads;
+  float4* raw = o.raw ? reinterpret_cast<float4*>(o.raw) + out0 : nullptr;
+  float4* nrm = o.norm ? reinterpret_cast<float4*>(o.norm) + out0 : nullptr;
+  uchar4* u8 = o.u8 ? reinterpret_cast<uchar4*>(o.u8) + out0 : nullptr;
+  for (unsigned q0 = blockIdx.x * (256 * BEV_FIN_UNROLL) + threadIdx.x; q0 < quads;
+       q0 += gridDim.x * (256 * BEV_FIN_UNROLL)) {
+    uint4 c[BEV_FIN_UNROLL];
+#pragma unroll
+    for (int k = 0; k < BEV_FIN_UNROLL; ++k) {
+      const unsigned q = q0 + k * 256;
+      c[k] = q < quads ? cp[q] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < BEV_FIN_UNROLL; ++k) {
+      const unsigned q = q0 + k * 256;
+      if (q >= quads) break;
+      if (c[k].x | c[k].y | c[k].z | c[k].w) cp[q] = make_uint4(0, 0, 0, 0);   // only dirty quads are rewritten
+      float4 r, n;
+      uchar4 b;
+      bev_cell(c[k].x, o.max_intensity, r.x, n.x, b.x);
+      bev_cell(c[k].y, o.max_intensity, r.y, n.y, b.y);
+      bev_cell(c[k].z, o.max_intensity, r.z, n.z, b.z);
+      bev_cell(c[k].w, o.max_intensity, r.w, n.w, b.w);
+      if (raw) lv_st_stream_f4(raw + q, r);
+      if (nrm) lv_st_stream_f4(nrm + q, n);
+      if (u8) u8[q] = b;
+    }
   }
 }
 
@@ -340,8 +354,10 @@ extern "C" int lv_bev_rasterize(lv_handle* h, const float* d_points, int32_t poi
       const int64_t items = (int64_t)o.n_frames * shape[0] * (shape[1] / 4);
       bev_finalize_hwc3_kernel<<<bev_grid(h, items, 8), 256, 0, stream>>>(p.counts, o);
     } else if (cells % 4 == 0) {
-      const int64_t items = (int64_t)o.n_frames * (cells / 4);
-      bev_finalize_flat4_kernel<<<bev_grid(h, items, 8), 256, 0, stream>>>(p.counts, o);
+      int gx = (int)lv_div_up(cells / 4, 256 * BEV_FIN_UNROLL);
+      const int want = (int)lv_div_up((int64_t)h->num_sms * 8, o.n_frames);
+      if (gx > want) gx = want < 1 ? 1 : want;
+      bev_finalize_flat4_kernel<<<dim3((unsigned)gx, (unsigned)o.n_frames), 256, 0, stream>>>(p.counts, o);
     } else {
       const int64_t items = (int64_t)o.n_frames * cells;
       bev_finalize_scalar_kernel<<<bev_grid(h, items, 8), 256, 0, stream>>>(p.counts, o);

@@ -1,0 +1,94 @@
+// Warp-level pillar decoration shared by the standalone decorate kernel
+// (lv_pillar.cu) and the fused voxelize+decorate gather (lv_voxel.cu).
+//
+// Reference arithmetic: second/second/pytorch/models/pointpillars.py:203-231
+// (+ variants :117-145, :290-319, :378-411); SURVEY.md Appendix A.3.
+#pragma once
+#include "lv_common.cuh"
+
+struct DecoCfg {
+  float vx, vy, x_off, y_off;  // pointpillars.py:198-201, rounded to float32 like torch does
+  int variant, with_distance;
+  int T, C_out;
+};
+
+__device__ __forceinline__ float lv_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float lv_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float lv_warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// one slot of one pillar -> C_out floats at o (C == 4 input features)
+__device__ __forceinline__ void lv_decorate_slot(const float4 q, bool live, float mx, float my, float mz, float cx,
+                                                 float cy, float height, const DecoCfg& d, float* o) {
+  if (!live) {  // padding mask (:226-231)
+    for (int c = 0; c < d.C_out; ++c) o[c] = 0.f;
+    return;
+  }
+  const float x = q.x, y = q.y, z = q.z;
+  const float px = x - cx, py = y - cy;  // f_center (:213-217)
+  int k = 0;
+  if (d.variant == LV_PILLAR_PFN) {
+    o[0] = x; o[1] = y; o[2] = z; o[3] = q.w;
+    k = 4;
+  } else if (d.variant == LV_PILLAR_OLD) {  // x,y overwritten in place before the concat
+    o[0] = px; o[1] = py; o[2] = z; o[3] = q.w;
+    k = 4;
+  } else {  // radius variants (:303-306): |xy|, z, features
+    o[0] = sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+    o[1] = z; o[2] = q.w;
+    k = 3;
+  }
+  o[k] = x - mx; o[k + 1] = y - my; o[k + 2] = z - mz;  // f_cluster (:210)
+  o[k + 3] = px; o[k + 4] = py;
+  k += 5;
+  if (d.variant == LV_PILLAR_RADIUS_HEIGHT) o[k++] = height;
+  if (d.with_distance) {
+    const float dx = (d.variant == LV_PILLAR_OLD) ? px : x, dy = (d.variant == LV_PILLAR_OLD) ? py : y;
+    o[k] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(z, z)));
+  }
+}
+
+// Decorates one pillar (T <= 64, C == 4) held in registers by one warp: lane owns slot
+// `lane` (a) and slot `lane + 32` (b); slots >= T must be passed as zeros.  The result,
+// T*C_out floats laid out [t][C_out], is staged in the warp's shared-memory region `st`
+// and then written to `dst` with contiguous (128-bit when aligned) stores.
+__device__ __forceinline__ void lv_decorate_warp(const float4 a, const float4 b, int num, int coor_y, int coor_x,
+                                                 const DecoCfg& d, float* st, float* __restrict__ dst, int lane) {
+  // mean over ALL T slots, padding zeros included (:208-209)
+  const float sx = lv_warp_sum(a.x + b.x), sy = lv_warp_sum(a.y + b.y), sz = lv_warp_sum(a.z + b.z);
+  const float fn = (float)num;
+  const float mx = __fdiv_rn(sx, fn), my = __fdiv_rn(sy, fn), mz = __fdiv_rn(sz, fn);
+  float height = 0.f;
+  if (d.variant == LV_PILLAR_RADIUS_HEIGHT) {  // :387-389, min/max over all T slots
+    const bool ha = lane < d.T, hb = lane + 32 < d.T;
+    const float zmax = fmaxf(ha ? a.z : -INFINITY, hb ? b.z : -INFINITY);
+    const float zmin = fminf(ha ? a.z : INFINITY, hb ? b.z : INFINITY);
+    height = lv_warp_max(zmax) - lv_warp_min(zmin);
+  }
+  // pillar centre: coors*vx + x_offset as a separate multiply and add (:213-217)
+  const float cx = __fadd_rn(__fmul_rn((float)coor_x, d.vx), d.x_off);
+  const float cy = __fadd_rn(__fmul_rn((float)coor_y, d.vy), d.y_off);
+  if (lane < d.T) lv_decorate_slot(a, lane < num, mx, my, mz, cx, cy, height, d, st + lane * d.C_out);
+  if (lane + 32 < d.T) lv_decorate_slot(b, lane + 32 < num, mx, my, mz, cx, cy, height, d, st + (lane + 32) * d.C_out);
+  __syncwarp();
+  const int per = d.T * d.C_out;
+  if ((per & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(st);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = lane; i < per / 4; i += 32) lv_st_stream_f4(d4 + i, s4[i]);
+  } else {
+    for (int i = lane; i < per; i += 32) dst[i] = st[i];
+  }
+  __syncwarp();
+}

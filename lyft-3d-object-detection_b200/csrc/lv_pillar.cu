@@ -15,6 +15,7 @@
 //   128-bit streaming stores; the memset of the reference is fused away.
 //   Algorithmic bytes: P*(C*4+16) read, B*C*ny*nx*4 written.
 #include "lv_common.cuh"
+#include "lv_decorate.cuh"
 
 #define PIL_WARPS 8
 
@@ -124,6 +125,25 @@ __global__ void __launch_bounds__(PIL_WARPS * 32) pillar_decorate_kernel(Decorat
   for (int64_t i = threadIdx.x; i < total; i += blockDim.x) dst[i] = stage[i];
 }
 
+// Fast path (C == 4, T <= 64): the pillar lives in registers (two float4 per lane), is read
+// exactly once, and leaves through the warp's shared-memory stage as 128-bit stores.
+__global__ void __launch_bounds__(PIL_WARPS * 32, 6) pillar_decorate_fast_kernel(DecorateParams p, DecoCfg d) {
+  extern __shared__ float stage[];  // [PIL_WARPS][T*C_out]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = d.T * d.C_out;
+  const int64_t warps_total = (int64_t)gridDim.x * PIL_WARPS;
+  float* st = stage + warp * per;
+  for (int64_t pil = (int64_t)blockIdx.x * PIL_WARPS + warp; pil < p.P; pil += warps_total) {
+    const float4* v = reinterpret_cast<const float4*>(p.voxels) + pil * d.T;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (lane < d.T) a = lv_ld_stream_f4(v + lane);
+    if (lane + 32 < d.T) b = lv_ld_stream_f4(v + lane + 32);
+    const int num = __ldg(p.num + pil);
+    const int4 co = __ldg(reinterpret_cast<const int4*>(p.coors) + pil);  // b, z, y, x
+    lv_decorate_warp(a, b, num, co.z, co.w, d, st, p.out + pil * per, lane);
+  }
+}
+
 // ---------------------------------------------------------------- scatter
 __global__ void __launch_bounds__(256) pillar_index_kernel(const int32_t* __restrict__ coords, int64_t P, int B, int ny,
                                                          int nx, int32_t* __restrict__ map) {
@@ -135,14 +155,17 @@ __global__ void __launch_bounds__(256) pillar_index_kernel(const int32_t* __rest
 }
 
 #define SC_TILE 128
-#define SC_PAD 1
+#define SC_LD (SC_TILE + 4)   // 16-byte aligned rows: the read-out is one conflict-free LDS.128 per lane
 
+// One CTA = one tile of 128 consecutive cells x all C channels of one sample.  Occupied
+// cells drop their feature row into the transposed shared-memory tile; the read-out masks
+// with the cell->pillar index, so the tile is never zero-filled.
 template <bool VEC>
 __global__ void __launch_bounds__(256) pillar_canvas_kernel(const float* __restrict__ feats, int32_t* __restrict__ map,
                                                           int C, int64_t ncell, int tiles_per_sample,
                                                           float* __restrict__ canvas) {
-  extern __shared__ float tile[];            // [C][SC_TILE + SC_PAD]
-  __shared__ int32_t idx[SC_TILE];
+  extern __shared__ __align__(16) float tile[];  // [C][SC_LD]
+  __shared__ __align__(16) int32_t idx[SC_TILE];
   const int b = blockIdx.x / tiles_per_sample;
   const int t = blockIdx.x - b * tiles_per_sample;
   const int64_t cell0 = (int64_t)t * SC_TILE;
@@ -159,11 +182,12 @@ __global__ void __launch_bounds__(256) pillar_canvas_kernel(const float* __restr
   const int any = __syncthreads_or(mine >= 0);
   float* dst = canvas + (int64_t)b * C * ncell + cell0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool full = VEC && n_here == SC_TILE;
   if (!any) {
     // empty tile: pure streaming zero fill
     for (int c = warp; c < C; c += 8) {
       float* row = dst + (int64_t)c * ncell;
-      if (VEC && n_here == SC_TILE) {
+      if (full) {
         lv_st_stream_f4(reinterpret_cast<float4*>(row) + lane, make_float4(0.f, 0.f, 0.f, 0.f));
       } else {
         for (int j = lane; j < n_here; j += 32) row[j] = 0.f;
@@ -171,24 +195,27 @@ __global__ void __launch_bounds__(256) pillar_canvas_kernel(const float* __restr
     }
     return;
   }
-  const int ld = SC_TILE + SC_PAD;
-  for (int i = threadIdx.x; i < C * ld; i += blockDim.x) tile[i] = 0.f;
-  __syncthreads();
   for (int j = warp; j < n_here; j += 8) {
     const int pi = idx[j];
     if (pi < 0) continue;
     const float* f = feats + (int64_t)pi * C;
-    for (int c = lane; c < C; c += 32) tile[c * ld + j] = __ldg(f + c);
+    for (int c = lane; c < C; c += 32) tile[c * SC_LD + j] = __ldg(f + c);
   }
   __syncthreads();
-  for (int c = warp; c < C; c += 8) {
-    float* row = dst + (int64_t)c * ncell;
-    const float* s = tile + c * ld;
-    if (VEC && n_here == SC_TILE) {
-      lv_st_stream_f4(reinterpret_cast<float4*>(row) + lane,
-                      make_float4(s[4 * lane], s[4 * lane + 1], s[4 * lane + 2], s[4 * lane + 3]));
-    } else {
-      for (int j = lane; j < n_here; j += 32) row[j] = s[j];
+  if (full) {
+    const int4 occ = reinterpret_cast<const int4*>(idx)[lane];
+    for (int c = warp; c < C; c += 8) {
+      float4 v = reinterpret_cast<const float4*>(tile + c * SC_LD)[lane];
+      v.x = occ.x >= 0 ? v.x : 0.f;
+      v.y = occ.y >= 0 ? v.y : 0.f;
+      v.z = occ.z >= 0 ? v.z : 0.f;
+      v.w = occ.w >= 0 ? v.w : 0.f;
+      lv_st_stream_f4(reinterpret_cast<float4*>(dst + (int64_t)c * ncell) + lane, v);
+    }
+  } else {
+    for (int c = warp; c < C; c += 8) {
+      float* row = dst + (int64_t)c * ncell;
+      for (int j = lane; j < n_here; j += 32) row[j] = idx[j] >= 0 ? tile[c * SC_LD + j] : 0.f;
     }
   }
 }
@@ -240,7 +267,14 @@ extern "C" int lv_pillar_decorate(lv_handle* h, const float* d_voxels, const int
   LV_REQUIRE(grid < (1ll << 31), "lv_pillar_decorate: too many pillars");
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool c4 = num_features == 4 && (reinterpret_cast<uintptr_t>(d_voxels) & 15) == 0;
-  if (c4) {
+  if (c4 && max_points <= 64) {
+    DecoCfg d{vx, vy, x_offset, y_offset, variant, with_distance ? 1 : 0, max_points, c_out};
+    if (smem > 48 * 1024)
+      LV_CHECK_CUDA(cudaFuncSetAttribute(pillar_decorate_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (int64_t)h->num_sms * 12;   // persistent-style: every warp loops over pillars
+    if (blocks > grid) blocks = grid;
+    pillar_decorate_fast_kernel<<<(unsigned)blocks, PIL_WARPS * 32, smem, stream>>>(p, d);
+  } else if (c4) {
     if (smem > 48 * 1024)
       LV_CHECK_CUDA(cudaFuncSetAttribute(pillar_decorate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pillar_decorate_kernel<true><<<(unsigned)grid, PIL_WARPS * 32, smem, stream>>>(p);
@@ -273,7 +307,7 @@ extern "C" int lv_pillar_scatter(lv_handle* h, const float* d_feats, const int32
     LV_LAUNCH_CHECK(h);
   }
   const int tiles = (int)lv_div_up(ncell, SC_TILE);
-  const size_t smem = (size_t)channels * (SC_TILE + SC_PAD) * sizeof(float);
+  const size_t smem = (size_t)channels * SC_LD * sizeof(float);
   LV_REQUIRE(smem <= 200 * 1024, "lv_pillar_scatter: too many channels (%d)", channels);
   const bool vec = (ncell % 4 == 0) && (reinterpret_cast<uintptr_t>(d_canvas) & 15) == 0;
   const int64_t grid = (int64_t)tiles * batch_size;

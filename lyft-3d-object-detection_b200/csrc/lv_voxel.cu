@@ -35,6 +35,7 @@
 #include <math.h>
 
 #include "lv_common.cuh"
+#include "lv_decorate.cuh"
 
 #define VX_THREADS 256
 #define VX_ITEMS 8
@@ -494,46 +495,80 @@ __global__ void __launch_bounds__(VX_THREADS) vx_heads_kernel(VoxParams p, const
 }
 
 // ---------------------------------------------------------------- K12: gather into voxels
-// LPV lanes cooperate on one voxel (32 for pillars, 8 for T=5).
+// LPV lanes cooperate on one voxel (32 for pillars, 8 for T=5).  grid = (GX, frames); the
+// voxel groups of a CTA loop over the frame's voxels, so no CTA is launched for rows that
+// do not exist (voxel_num is only known on the device).
 template <int LPV, bool C4>
 __global__ void __launch_bounds__(VX_THREADS) vx_gather_kernel(VoxParams p, const int32_t* __restrict__ vals) {
   const int fl = blockIdx.y, f = p.f0 + fl;
   const int sub = threadIdx.x % LPV;
-  const int v = (int)(((int64_t)blockIdx.x * VX_THREADS + threadIdx.x) / LPV);
-  if (v >= p.V) return;
   const int vnum = p.voxel_num[f];
-  if (v >= vnum && (!p.zero_tail || p.concat)) return;
-  const int64_t row = p.row_base[f] + v;
-  if (row >= p.capacity) return;
-  float* out = p.voxels + row * p.T * p.C;
-  int n = 0;
-  int s = 0;
-  if (v < vnum) {
-    s = p.seg_start[(int64_t)fl * p.V + v];
-    n = p.seg_end[(int64_t)fl * p.V + v] - s;
-    if (n > p.T) n = p.T;
-  }
-  if (sub == 0) {
-    p.num_points[row] = n;
-    if (v >= vnum) {
-      int32_t* co = p.coords + row * p.coord_cols;
-      for (int j = 0; j < p.coord_cols; ++j) co[j] = 0;
-    }
-  }
+  const int limit = (p.zero_tail && !p.concat) ? p.V : vnum;
+  const int64_t row0 = p.row_base[f];
   const int64_t fstart = __ldg(p.frame_off + f);
-  const int32_t* vv = vals + (fstart - p.pt_lo) + s;
-  if (C4) {
-    float4* o4 = reinterpret_cast<float4*>(out);
-    for (int t = sub; t < p.T; t += LPV) {
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < n) q = __ldg(reinterpret_cast<const float4*>(p.pts) + fstart + vv[t]);
-      o4[t] = q;
+  const int groups = VX_THREADS / LPV;
+  for (int v = blockIdx.x * groups + threadIdx.x / LPV; v < limit; v += gridDim.x * groups) {
+    const int64_t row = row0 + v;
+    if (row >= p.capacity) break;
+    float* out = p.voxels + row * p.T * p.C;
+    int n = 0;
+    int s = 0;
+    if (v < vnum) {
+      s = p.seg_start[(int64_t)fl * p.V + v];
+      n = p.seg_end[(int64_t)fl * p.V + v] - s;
+      if (n > p.T) n = p.T;
     }
-  } else {
-    for (int t = sub; t < p.T; t += LPV) {
-      const float* src = (t < n) ? p.pts + (fstart + vv[t]) * p.C : nullptr;
-      for (int c = 0; c < p.C; ++c) out[t * p.C + c] = src ? __ldg(src + c) : 0.f;
+    if (sub == 0) {
+      p.num_points[row] = n;
+      if (v >= vnum) {
+        int32_t* co = p.coords + row * p.coord_cols;
+        for (int j = 0; j < p.coord_cols; ++j) co[j] = 0;
+      }
     }
+    const int32_t* vv = vals + (fstart - p.pt_lo) + s;
+    if (C4) {
+      float4* o4 = reinterpret_cast<float4*>(out);
+      for (int t = sub; t < p.T; t += LPV) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < n) q = __ldg(reinterpret_cast<const float4*>(p.pts) + fstart + vv[t]);
+        lv_st_stream_f4(o4 + t, q);
+      }
+    } else {
+      for (int t = sub; t < p.T; t += LPV) {
+        const float* src = (t < n) ? p.pts + (fstart + vv[t]) * p.C : nullptr;
+        for (int c = 0; c < p.C; ++c) out[t * p.C + c] = src ? __ldg(src + c) : 0.f;
+      }
+    }
+  }
+}
+
+// K12': gather fused with the PillarFeatureNet decoration (pointpillars.py:203-231): the
+// (P,T,4) voxel tensor is never written; one warp per pillar pulls its <= T points through
+// the sorted index list straight into registers and emits the decorated (T,C_out) block.
+__global__ void __launch_bounds__(VX_THREADS, 6) vx_gather_decorate_kernel(VoxParams p, const int32_t* __restrict__ vals,
+                                                                          DecoCfg d, float* __restrict__ decorated) {
+  extern __shared__ float stage[];  // [8 warps][T*C_out]
+  const int fl = blockIdx.y, f = p.f0 + fl;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vnum = p.voxel_num[f];
+  const int64_t row0 = p.row_base[f];
+  const int64_t fstart = __ldg(p.frame_off + f);
+  const int per = d.T * d.C_out;
+  float* st = stage + warp * per;
+  const float4* pts4 = reinterpret_cast<const float4*>(p.pts) + fstart;
+  for (int v = blockIdx.x * (VX_THREADS / 32) + warp; v < vnum; v += gridDim.x * (VX_THREADS / 32)) {
+    const int64_t row = row0 + v;
+    if (row >= p.capacity) break;
+    const int s = p.seg_start[(int64_t)fl * p.V + v];
+    int n = p.seg_end[(int64_t)fl * p.V + v] - s;
+    if (n > d.T) n = d.T;
+    const int32_t* vv = vals + (fstart - p.pt_lo) + s;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (lane < n) a = __ldg(pts4 + vv[lane]);
+    if (lane + 32 < n) b = __ldg(pts4 + vv[lane + 32]);
+    const int4 co = *reinterpret_cast<const int4*>(p.coords + row * 4);  // b, z, y, x (written by K4)
+    if (lane == 0) p.num_points[row] = n;
+    lv_decorate_warp(a, b, n, co.z, co.w, d, st, decorated + row * per, lane);
   }
 }
 
@@ -573,7 +608,8 @@ static int vx_bits_for(int v) {  // bits needed for ids in [0, v)
 
 static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
                   const int64_t* h_frame_offsets, float* d_voxels, int32_t* d_coords, int32_t* d_num_points,
-                  int32_t* d_voxel_num, int concat, int64_t capacity, int64_t* d_row_base, lv_stream stream_) {
+                  int32_t* d_voxel_num, int concat, int64_t capacity, int64_t* d_row_base, const DecoCfg* deco,
+                  float* d_decorated, lv_stream stream_) {
   LV_REQUIRE(h != nullptr, "lv_voxelize: null handle");
   LV_REQUIRE(cfg && h_frame_offsets, "lv_voxelize: null config / frame offsets");
   LV_REQUIRE(n_frames >= 0, "lv_voxelize: negative frame count");
@@ -589,7 +625,10 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   LV_REQUIRE(G < (1ll << 28), "lv_voxelize: grid of %lld cells exceeds the dense-map limit (2^28)", (long long)G);
   LV_REQUIRE(n_frames == 0 || h_frame_offsets[0] == 0, "lv_voxelize: frame_offsets[0] must be 0");
   if (n_frames == 0) return LV_OK;
-  LV_REQUIRE(d_voxels && d_coords && d_num_points && d_voxel_num, "lv_voxelize: null output");
+  LV_REQUIRE((d_voxels || deco) && d_coords && d_num_points && d_voxel_num, "lv_voxelize: null output");
+  LV_REQUIRE(!deco || (d_decorated && concat && cfg->num_features == 4 && cfg->max_points <= 64 &&
+                       (reinterpret_cast<uintptr_t>(d_points) & 15) == 0),
+             "lv_pillarize_concat: needs 4 features per point, max_points <= 64 and 16-byte aligned points");
   const int V = cfg->max_voxels, T = cfg->max_points, C = cfg->num_features;
 
   // chunk prefix per frame (a frame with no points still owns zero chunks)
@@ -717,9 +756,22 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
       vx_heads_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p, sorted_keys);
       LV_LAUNCH_CHECK(h);
     }
-    {
+    if (deco) {
+      const size_t smem = (size_t)(VX_THREADS / 32) * T * deco->C_out * sizeof(float);
+      if (smem > 48 * 1024)
+        LV_CHECK_CUDA(cudaFuncSetAttribute(vx_gather_decorate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int gx = (int)lv_div_up((int64_t)h->num_sms * 12, nf);
+      if (gx < 8) gx = 8;
+      dim3 grid_g((unsigned)gx, (unsigned)nf);
+      vx_gather_decorate_kernel<<<grid_g, VX_THREADS, smem, stream>>>(p, sorted_vals, *deco, d_decorated);
+      LV_LAUNCH_CHECK(h);
+    } else {
       const int lpv = T >= 24 ? 32 : (T >= 12 ? 16 : 8);
-      dim3 grid_g((unsigned)lv_div_up((int64_t)V * lpv, VX_THREADS), (unsigned)nf);
+      const int64_t full = lv_div_up((int64_t)V * lpv, VX_THREADS);
+      int64_t gx = lv_div_up((int64_t)h->num_sms * 16, nf);
+      if (gx < 8) gx = 8;
+      if (gx > full) gx = full;
+      dim3 grid_g((unsigned)gx, (unsigned)nf);
       if (out4) {
         if (lpv == 32) vx_gather_kernel<32, true><<<grid_g, VX_THREADS, 0, stream>>>(p, sorted_vals);
         else if (lpv == 16) vx_gather_kernel<16, true><<<grid_g, VX_THREADS, 0, stream>>>(p, sorted_vals);
@@ -744,7 +796,7 @@ extern "C" int lv_voxelize(lv_handle* h, const lv_voxel_config* cfg, const float
                            const int64_t* h_frame_offsets, float* d_voxels, int32_t* d_coords, int32_t* d_num_points,
                            int32_t* d_voxel_num, lv_stream stream) {
   return vx_run(h, cfg, d_points, n_frames, h_frame_offsets, d_voxels, d_coords, d_num_points, d_voxel_num, 0, 0,
-                nullptr, stream);
+                nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int lv_voxelize_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
@@ -754,7 +806,22 @@ extern "C" int lv_voxelize_concat(lv_handle* h, const lv_voxel_config* cfg, cons
   LV_REQUIRE(capacity_rows >= 0, "lv_voxelize_concat: negative capacity");
   LV_REQUIRE(n_frames == 0 || d_voxel_offsets, "lv_voxelize_concat: null voxel_offsets");
   return vx_run(h, cfg, d_points, n_frames, h_frame_offsets, d_voxels, d_coords4, d_num_points, d_voxel_num, 1,
-                capacity_rows, d_voxel_offsets, stream);
+                capacity_rows, d_voxel_offsets, nullptr, nullptr, stream);
+}
+
+extern "C" int lv_pillarize_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
+                                   const int64_t* h_frame_offsets, int64_t capacity_rows, float vx, float vy,
+                                   float x_offset, float y_offset, int32_t variant, int32_t with_distance,
+                                   float* d_decorated, int32_t* d_coords4, int32_t* d_num_points, int32_t* d_voxel_num,
+                                   int64_t* d_voxel_offsets, lv_stream stream) {
+  LV_REQUIRE(cfg != nullptr, "lv_pillarize_concat: null config");
+  LV_REQUIRE(capacity_rows >= 0, "lv_pillarize_concat: negative capacity");
+  LV_REQUIRE(n_frames == 0 || d_voxel_offsets, "lv_pillarize_concat: null voxel_offsets");
+  const int c_out = lv_pillar_out_channels(cfg->num_features, variant, with_distance);
+  LV_REQUIRE(c_out > 0, "lv_pillarize_concat: bad variant %d", variant);
+  DecoCfg d{vx, vy, x_offset, y_offset, variant, with_distance ? 1 : 0, cfg->max_points, c_out};
+  return vx_run(h, cfg, d_points, n_frames, h_frame_offsets, nullptr, d_coords4, d_num_points, d_voxel_num, 1,
+                capacity_rows, d_voxel_offsets, &d, d_decorated, stream);
 }
 
 extern "C" int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const float* h_points, int32_t n_frames,

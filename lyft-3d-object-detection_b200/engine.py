@@ -84,6 +84,14 @@ class FrameBatchEngine:
             self.voxels.data_ptr(), self.coords.data_ptr(), self.num_points.data_ptr(), self.voxel_num.data_ptr(),
             self.voxel_offsets.data_ptr(), st))
 
+    def pillarize(self, points):
+        """voxelize + decorate fused (lv_pillarize_concat): the (P,T,4) voxel tensor is never written."""
+        st = nat.current_stream_ptr(self.dev)
+        nat.check(self.lib.lv_pillarize_concat(
+            self.h.ptr, ctypes.byref(self.cfg), points.data_ptr(), self.F, self.offsets.ctypes.data, self.cap,
+            self.vx, self.vy, self.x_off, self.y_off, 0, 0, self.decorated.data_ptr(), self.coords.data_ptr(),
+            self.num_points.data_ptr(), self.voxel_num.data_ptr(), self.voxel_offsets.data_ptr(), st))
+
     def read_total_rows(self):
         """The one host read of the pillar path: total pillars of the batch (the
         reference keeps num_voxels on the host too, preprocess.py:310)."""
@@ -106,12 +114,16 @@ class FrameBatchEngine:
             self.h.ptr, feats.data_ptr(), self.coords.data_ptr(), rows, self.channels, self.F, self.ny, self.nx,
             self.canvas.data_ptr(), st))
 
-    def step(self, points, pfn=None):
+    def step(self, points, pfn=None, fused=True):
         """One pass of both paths over a (F*n, 4) float32 CUDA tensor of points."""
         self.bev(points)
-        self.voxelize(points)
-        rows = self.read_total_rows()
-        self.decorate(rows)
+        if fused:
+            self.pillarize(points)
+            rows = self.read_total_rows()
+        else:
+            self.voxelize(points)
+            rows = self.read_total_rows()
+            self.decorate(rows)
         feats = None
         if pfn is not None:
             feats = pfn(self.decorated[:rows])

@@ -1,0 +1,100 @@
+"""GPU parity of the batched engine entry points: device-side batch assembly
+(lv_voxelize_concat), the fused voxelize+decorate (lv_pillarize_concat) and the whole
+FrameBatchEngine step, against the oracle chain run frame by frame."""
+import numpy as np
+import pytest
+
+from lyft3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-6, 1e-5   # see tests/test_gpu_pillar.py
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import torch
+    assert torch.cuda.is_available()
+    from lyft3d_b200.engine import FrameBatchEngine
+    from oracle import bev_oracle, pillar_oracle, voxel_oracle
+    F, n = 6, 20000
+    frames = [synth.c5_frame(f)[:n] for f in range(F)]
+    eng = FrameBatchEngine(0, F, n)
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    return eng, frames, pts, bev_oracle, pillar_oracle, voxel_oracle
+
+
+def test_concat_voxelize_equals_merge_second_batch(setup):
+    eng, frames, pts, bo, po, vo = setup
+    eng.voxelize(pts)
+    rows = eng.read_total_rows()
+    orc = vo.VoxelOracle(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)
+    res = [orc.generate(fr) for fr in frames]
+    ref_v = np.concatenate([r[0] for r in res])
+    ref_c = po.merge_batch_coords([r[1] for r in res])          # preprocess.py:44-50
+    ref_n = np.concatenate([r[2] for r in res])
+    assert rows == ref_v.shape[0]
+    assert eng.voxel_num.cpu().tolist() == [r[0].shape[0] for r in res]
+    offs = eng.voxel_offsets.cpu().numpy()
+    assert offs.tolist() == np.concatenate([[0], np.cumsum([r[0].shape[0] for r in res])]).tolist()
+    assert np.array_equal(eng.voxels[:rows].cpu().numpy().view(np.uint32), ref_v.view(np.uint32))
+    assert np.array_equal(eng.coords[:rows].cpu().numpy(), ref_c)
+    assert np.array_equal(eng.num_points[:rows].cpu().numpy(), ref_n)
+
+
+def test_fused_pillarize_equals_voxelize_then_decorate(setup):
+    eng, frames, pts, bo, po, vo = setup
+    eng.voxelize(pts)
+    rows = eng.read_total_rows()
+    eng.decorate(rows)
+    unfused = eng.decorated[:rows].clone()
+    coords = eng.coords[:rows].clone()
+    eng.decorated.zero_()
+    eng.pillarize(pts)
+    assert eng.read_total_rows() == rows
+    fused = eng.decorated[:rows]
+    assert bool((fused == unfused).all())                       # same warp-level arithmetic: identical bits
+    assert bool((eng.coords[:rows] == coords).all())
+    orc = vo.VoxelOracle(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)
+    res = [orc.generate(fr) for fr in frames]
+    ref = po.decorate(np.concatenate([r[0] for r in res]), np.concatenate([r[2] for r in res]),
+                      po.merge_batch_coords([r[1] for r in res]), synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE)
+    np.testing.assert_allclose(fused.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+
+
+def test_full_step_vs_cpu_path(setup):
+    import torch
+    eng, frames, pts, bo, po, vo = setup
+    torch.manual_seed(3)
+    eng.features.copy_(torch.randn_like(eng.features))
+    rows = eng.step(pts)
+    feats = eng.features[:rows].cpu().numpy()
+    orc = vo.VoxelOracle(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)
+    coords = po.merge_batch_coords([orc.generate(fr)[1] for fr in frames])
+    ref_canvas = po.scatter(feats, coords, len(frames), 400, 400)
+    assert np.array_equal(eng.canvas.cpu().numpy(), ref_canvas)
+    for f, fr in enumerate(frames):
+        bev = bo.create_voxel_pointcloud(np.ascontiguousarray(fr.T), synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE,
+                                         synth.BEV_Z_OFFSET)
+        norm = bo.normalize_voxel_intensities(bev)
+        assert np.array_equal(eng.bev_norm[f].cpu().numpy(), norm)
+        assert np.array_equal(eng.bev_u8[f].cpu().numpy(), bo.quantize_u8(norm))
+
+
+def test_capacity_overflow_is_reported(setup):
+    import torch
+    from lyft3d_b200 import _native as nat
+    from lyft3d_b200.engine import FrameBatchEngine
+    eng, frames, pts, *_ = setup
+    small = FrameBatchEngine(0, eng.F, eng.n, voxel_capacity=1000)
+    small.voxelize(pts)
+    with pytest.raises(nat.LyftVoxelError):
+        small.read_total_rows()
+    torch.cuda.synchronize()
+
+
+def test_shard_frames():
+    from lyft3d_b200.engine import shard_frames
+    got = sorted(sum((shard_frames(8192, r, 8) for r in range(8)), []))
+    assert got == list(range(8192))
+    assert shard_frames(10, 1, 4) == [1, 5, 9]
