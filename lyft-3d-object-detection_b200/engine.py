@@ -129,3 +129,75 @@ class FrameBatchEngine:
             feats = pfn(self.decorated[:rows])
         self.scatter(rows, feats)
         return rows
+
+
+class HostPipeline:
+    """End-to-end driver with HOST buffers on both sides of a FrameBatchEngine.
+
+    Pinned host points are copied in on a copy stream, both paths run on the compute
+    stream, and the BEV u8 images + per-frame pillar counts are copied back to pinned host
+    memory on a third stream; the H2D of step i+1 and the D2H of step i-1 overlap the
+    kernels of step i (two device input slots).  The canvas stays on the device - its
+    consumer is the RPN (second/second/pytorch/models/voxelnet.py:336).
+    """
+
+    def __init__(self, engine, fused=True):
+        self.eng = engine
+        self.fused = fused
+        dev = engine.dev
+        n_rows = engine.F * engine.n
+        self.s_in = torch.cuda.Stream(dev)
+        self.s_out = torch.cuda.Stream(dev)
+        self.dev_pts = [torch.empty((n_rows, 4), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]      # H2D of slot done
+        self.ev_free = [torch.cuda.Event() for _ in range(2)]    # kernels reading slot done
+        self.ev_bev = torch.cuda.Event()                         # BEV outputs of the step ready
+        self.ev_out = torch.cuda.Event()                         # D2H of the step done
+        self.host_u8 = torch.empty(engine.bev_u8.shape, dtype=torch.uint8, pin_memory=True)
+        self.host_vnum = torch.empty((engine.F,), dtype=torch.int32, pin_memory=True)
+        self.h2d_bytes = n_rows * 16
+        self.d2h_bytes = self.host_u8.numel() + self.host_vnum.numel() * 4
+
+    def _issue_h2d(self, slot, host_pts):
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_free[slot])
+            self.dev_pts[slot].copy_(host_pts, non_blocking=True)
+            self.ev_in[slot].record(self.s_in)
+
+    def run(self, host_batches, steps):
+        """Processes `steps` batches (host_batches[i % len]) and returns when every
+        result of the last step is in host memory."""
+        eng = self.eng
+        cur = torch.cuda.current_stream(eng.dev)
+        for ev in self.ev_free:
+            ev.record(cur)
+        self.ev_out.record(cur)
+        self._issue_h2d(0, host_batches[0])
+        rows = 0
+        for i in range(steps):
+            slot = i & 1
+            if i + 1 < steps:
+                self._issue_h2d(slot ^ 1, host_batches[(i + 1) % len(host_batches)])
+            cur.wait_event(self.ev_in[slot])
+            pts = self.dev_pts[slot]
+            # pillar path first: it does not touch the BEV buffers still being copied out
+            if self.fused:
+                eng.pillarize(pts)
+                rows = eng.read_total_rows()
+            else:
+                eng.voxelize(pts)
+                rows = eng.read_total_rows()
+                eng.decorate(rows)
+            eng.scatter(rows)
+            cur.wait_event(self.ev_out)          # previous step's images have left the device
+            eng.bev(pts)
+            self.ev_free[slot].record(cur)
+            self.ev_bev.record(cur)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_bev)
+                self.host_u8.copy_(eng.bev_u8, non_blocking=True)
+                self.host_vnum.copy_(eng.voxel_num, non_blocking=True)
+                self.ev_out.record(self.s_out)
+        self.ev_out.synchronize()
+        cur.synchronize()
+        return rows
