@@ -6,45 +6,50 @@
 //
 // The reference is a serial loop: voxel ids are handed out in order of first
 // appearance, slots inside a voxel in point order.  Atomics give arbitrary order,
-// so order is RECONSTRUCTED (all per frame, many frames per launch):
+// so order is RECONSTRUCTED, per frame, many frames per launch, in six kernels:
 //
-//   K1 cells      cell(i) = ((cz*gy)+cy)*gx+cx from floorf((p-lo)/vs) (fp32 IEEE sub/div);
-//                 first[cell] = atomicMin(point index)   (warp-aggregated)
-//   K2 count      creator(i) := first[cell(i)] == i ; per-chunk creator counts
-//   K3 scan       per-frame exclusive scan of the chunk counts -> voxel_num = min(total, V)
-//   K4 assign     rank(i) = #creators before i = voxel id; coords[rank] = (z,y,x);
-//                 first[cell] := ~rank; `break` cut-off = index of the creator of rank V
-//   K5 keys       vid(i) = ~first[cell(i)]; kept(i) = vid < V and i < cut;
-//                 digit histogram of pass 1
-//   K6..K10       stable LSD radix sort of the kept points by voxel id (2 passes of
-//                 <= 9 bits, 3 beyond 2^18 voxels): chunk histogram -> per-frame scan
-//                 -> stable in-chunk rank (warp match + per-warp digit counters) + scatter.
-//                 Stability makes the order inside a voxel the point order for free.
-//   K11 heads     segment [start,end) of every voxel in the sorted list
-//   K12 gather    one (sub)warp per voxel: the first min(count,T) points of its segment
-//                 are copied into voxels[v, slot, :], the rest of the row is zero-filled,
-//                 num_points[v] = min(count, T).  Every output byte is written once.
-//   K13 reset     creators put EMPTY back into first[] (touched-cell reset) so the
-//                 dense map never needs a memset.
+//   K1 cells     cell(i) = ((cz*gy)+cy)*gx+cx from floorf((p-lo)/vs) (fp32 IEEE sub/div);
+//                first[cell] = atomicMin(point index)                 (warp-aggregated)
+//   K2 assign    creator(i) := first[cell(i)] == i.  Single-pass scan of the creator flags
+//                (decoupled look-back over the chunks of the frame): rank(i) = voxel id.
+//                first[cell] := ~rank, creator_cell[rank] = cell, voxel_num = min(total, V),
+//                `break` cut-off = index of the creator of rank V.
+//   K3 keys      vid(i) = ~first[cell(i)]; kept(i) = vid < V and i < cut; per-chunk histogram
+//                of the HIGH digit vid >> L (a "bin" = 2^L consecutive voxel ids)
+//   K4 scan      per-frame exclusive scan of the [bin][chunk] histogram
+//   K5 scatter   stable multi-split of the kept points into their bins (warp match +
+//                per-warp digit counters); creators put EMPTY back into first[]
+//                (touched-cell reset, so the dense map never needs a memset)
+//   K6 bins      one CTA per (frame, bin): stable rank by the LOW digit inside shared memory
+//                -> slot = number of earlier points of the same voxel; the first T point
+//                indices of each of the 2^L voxels land in a shared-memory slot table; then
+//                one (sub)warp per voxel gathers its points and writes the output row -
+//                either the raw (T,C) voxel, or, fused, the PillarFeatureNet decoration
+//                (T,C_out) (pointpillars.py:203-231) - plus num_points and coordinates.
+//                Every output byte is written exactly once.
+//
+// Stability of K5 and K6 makes the order inside a voxel the point order for free.
 //
 // HBM layout: points (N,C) f32 rows; workspace per sub-batch of frames: first[] dense
-// int32 map [frames_in_flight][gz*gy*gx] (all EMPTY between calls), cell[] int32,
-// key/val ping-pong buffers, chunk histograms.  Outputs padded per frame:
-// voxels (F,V,T,C) f32, coords (F,V,3) i32 zyx, num_points (F,V) i32, voxel_num (F) i32.
-// Algorithmic bytes: 4*C per point read + V*(T*C*4 + 16) written.
+// int32 map [frames_in_flight][gz*gy*gx] (all EMPTY between calls), cell[], key0[],
+// one (key,val) list, creator_cell[], [bin][chunk] histograms, look-back descriptors.
+// Outputs padded per frame (lv_voxelize) or concatenated with a batch column
+// (lv_voxelize_concat / lv_pillarize_concat = merge_second_batch on the device).
+// Algorithmic bytes: 4*C per point read + V*(T*C*4 + 16) written (T*C_out*4 when fused).
 #include <math.h>
 
 #include "lv_common.cuh"
 #include "lv_decorate.cuh"
 
 #define VX_THREADS 256
+#define VX_WARPS (VX_THREADS / 32)
 #define VX_ITEMS 8
 #define VX_CHUNK (VX_THREADS * VX_ITEMS)  // 2048 points per chunk; chunks never straddle frames
 #define VX_EMPTY 0x7f7f7f7f               // memset-able "no point yet"
 #define VX_CREATOR_BIT 0x40000000         // flag kept in cell[] (grid cells < 2^28)
-#define VX_MAX_DIGIT_BITS 9
-#define VX_MAX_DIGITS (1 << VX_MAX_DIGIT_BITS)
 #define VX_DROPPED 0xffffffffu
+#define VX_MAX_BINS 2048
+#define VX_MAX_LOW_BITS 10
 
 struct VoxParams {
   const float* pts;            // (N_total, C)
@@ -58,22 +63,20 @@ struct VoxParams {
   int grid[3];                 // gx, gy, gz
   int64_t G;                   // cells per frame
   int T, V, overflow, zero_tail;
-  // workspace
+  int low_bits, n_bins;        // bin = vid >> low_bits
+  // workspace (indexed relative to the sub-batch)
   int32_t* map;                // [f1-f0][G]
-  int32_t* cell;               // [points in sub-batch]
-  uint32_t* key0;              // pass-0 keys (vid or VX_DROPPED), indexed like cell
-  uint32_t* keyA; int32_t* valA;
-  uint32_t* keyB; int32_t* valB;
-  int32_t* chunk_cnt;          // [chunks in sub-batch] creator counts -> exclusive bases
-  int32_t* hist;               // [chunks in sub-batch * digits]
-  int32_t* frame_total;        // [frames in sub-batch] creators
-  int32_t* frame_cut;          // [frames in sub-batch] break cut-off (local index)
-  int32_t* frame_kept;         // [frames in sub-batch] kept points
-  int32_t* seg_start;          // [frames in sub-batch][V]
-  int32_t* seg_end;
+  int32_t* cell;               // [points]
+  uint32_t* key0;              // [points] vid or VX_DROPPED
+  uint32_t* keys; int32_t* vals;  // [points] kept points grouped by bin (per frame, at the frame's start)
+  int32_t* creator_cell;       // [points] cell of voxel `rank` of a frame at [frame start + rank]
+  unsigned long long* chunk_state;  // [chunks] look-back descriptors (flag << 62 | value)
+  int32_t* hist;               // [chunks * n_bins], per frame laid out [bin][chunk]
+  int32_t* frame_cut;          // [frames] break cut-off (local index)
+  int32_t* frame_kept;         // [frames] kept points
   // outputs
   float* voxels; int32_t* coords; int32_t* num_points; int32_t* voxel_num;
-  int64_t* row_base;           // [F+1] first output row of every frame (padded: f*V; concat: prefix of voxel_num)
+  int64_t* row_base;           // [F+1] first output row of every frame (concat: prefix of voxel_num)
   int concat;                  // 1: frames back to back, coords carry the batch index (coord_cols == 4)
   int coord_cols;              // 3 (z,y,x) or 4 (b,z,y,x)
   int64_t capacity;            // output rows available
@@ -117,6 +120,10 @@ __global__ void __launch_bounds__(VX_THREADS) vx_cells_kernel(VoxParams p) {
   __shared__ int sm[4];
   const ChunkLoc L = vx_locate(p, sm);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    p.chunk_state[blockIdx.x] = 0ull;                // look-back descriptor of this chunk: invalid
+    if (L.c == 0) p.frame_cut[L.fl] = 0x7fffffff;
+  }
   int32_t* map = p.map + (int64_t)L.fl * p.G;
   const int base = L.c * VX_CHUNK + warp * (32 * VX_ITEMS);
 #pragma unroll 2
@@ -148,121 +155,23 @@ __global__ void __launch_bounds__(VX_THREADS) vx_cells_kernel(VoxParams p) {
   }
 }
 
-// ---------------------------------------------------------------- K2: creators per chunk
-__device__ __forceinline__ int vx_block_sum(int v, int* sm_warp /*[8]*/) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) sm_warp[threadIdx.x >> 5] = v;
-  __syncthreads();
-  int t = 0;
-#pragma unroll
-  for (int w = 0; w < VX_THREADS / 32; ++w) t += sm_warp[w];
-  return t;
+// ---------------------------------------------------------------- K2: voxel ids (single-pass scan)
+#define VX_FLAG_AGG (1ull << 62)
+#define VX_FLAG_PREFIX (2ull << 62)
+
+__device__ __forceinline__ unsigned long long vx_ld_state(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void vx_st_state(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(VX_THREADS) vx_count_kernel(VoxParams p) {
-  __shared__ int sm[4];
-  __shared__ int sw[VX_THREADS / 32];
-  const ChunkLoc L = vx_locate(p, sm);
-  const int32_t* map = p.map + (int64_t)L.fl * p.G;
-  const int base = L.c * VX_CHUNK;
-  int cnt = 0;
-#pragma unroll
-  for (int k = 0; k < VX_ITEMS; ++k) {
-    const int li = base + k * VX_THREADS + threadIdx.x;
-    if (li < L.n) {
-      const int cell = p.cell[L.start + li - p.pt_lo];
-      if (cell >= 0 && map[cell] == li) ++cnt;
-    }
-  }
-  const int total = vx_block_sum(cnt, sw);
-  if (threadIdx.x == 0) p.chunk_cnt[blockIdx.x] = total;
-}
-
-// ---------------------------------------------------------------- block exclusive scan helper
-// in-place exclusive scan of `n` ints by one CTA (VX_THREADS threads); returns the total.
-__device__ int vx_cta_exclusive_scan(int32_t* data, int n, int* sw /*[8]*/, int* carry_sm) {
-  if (threadIdx.x == 0) *carry_sm = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < n; base += VX_THREADS * 4) {
-    int v[4];
-    int s = 0;
-    const int i0 = base + threadIdx.x * 4;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = (i0 + k < n) ? data[i0 + k] : 0;
-      s += v[k];
-    }
-    int inc = s;  // inclusive warp scan of the thread sums
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) sw[warp] = inc;
-    __syncthreads();
-    int woff = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < VX_THREADS / 32; ++w) {
-      const int t = sw[w];
-      if (w < warp) woff += t;
-      tile_total += t;
-    }
-    int run = *carry_sm + woff + inc - s;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (i0 + k < n) data[i0 + k] = run;
-      run += v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *carry_sm += tile_total;
-    __syncthreads();
-  }
-  return *carry_sm;
-}
-
-// ---------------------------------------------------------------- K3: per-frame scan of chunk counts
-__global__ void __launch_bounds__(VX_THREADS) vx_scan_chunks_kernel(VoxParams p) {
-  __shared__ int sw[VX_THREADS / 32];
-  __shared__ int carry;
-  const int fl = blockIdx.x, f = p.f0 + fl;
-  const int cb = __ldg(p.frame_chunk + f) - p.chunk_lo;
-  const int nch = __ldg(p.frame_chunk + f + 1) - __ldg(p.frame_chunk + f);
-  const int total = vx_cta_exclusive_scan(p.chunk_cnt + cb, nch, sw, &carry);
-  if (threadIdx.x == 0) {
-    p.frame_total[fl] = total;
-    p.frame_cut[fl] = 0x7fffffff;
-    p.voxel_num[f] = total < p.V ? total : p.V;
-    if (!p.concat) {
-      p.row_base[f] = (int64_t)f * p.V;
-      if (f + 1 == p.f1) p.row_base[f + 1] = (int64_t)(f + 1) * p.V;
-    }
-  }
-}
-
-// concat layout (merge_second_batch, second/second/data/preprocess.py:28-50): row_base = prefix of voxel_num
-__global__ void vx_row_base_kernel(VoxParams p) {
-  const int lane = threadIdx.x;
-  int64_t carry = p.row_base[p.f0];
-  for (int b = p.f0; b < p.f1; b += 32) {
-    const int f = b + lane;
-    int v = f < p.f1 ? p.voxel_num[f] : 0;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (f < p.f1) p.row_base[f + 1] = carry + inc;
-    carry += __shfl_sync(0xffffffffu, inc, 31);
-  }
-}
-
-// ---------------------------------------------------------------- K4: voxel ids for creators
 __global__ void __launch_bounds__(VX_THREADS) vx_assign_kernel(VoxParams p) {
   __shared__ int sm[4];
-  __shared__ int sw[VX_THREADS / 32];
+  __shared__ int sw[VX_WARPS];
+  __shared__ int s_excl;
   const ChunkLoc L = vx_locate(p, sm);
   int32_t* map = p.map + (int64_t)L.fl * p.G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -291,14 +200,52 @@ __global__ void __launch_bounds__(VX_THREADS) vx_assign_kernel(VoxParams p) {
   }
   if (lane == 31) sw[warp] = inc;
   __syncthreads();
-  int woff = 0;
+  int woff = 0, agg = 0;
 #pragma unroll
-  for (int w = 0; w < VX_THREADS / 32; ++w)
+  for (int w = 0; w < VX_WARPS; ++w) {
     if (w < warp) woff += sw[w];
-  int rank = p.chunk_cnt[blockIdx.x] + woff + inc - s;
+    agg += sw[w];
+  }
+  // decoupled look-back over the previous chunks of this frame (warp 0)
+  if (warp == 0) {
+    unsigned long long* st = p.chunk_state + blockIdx.x;
+    int excl = 0;
+    if (L.c == 0) {
+      if (lane == 0) vx_st_state(st, VX_FLAG_PREFIX | (unsigned)agg);
+    } else {
+      if (lane == 0) vx_st_state(st, VX_FLAG_AGG | (unsigned)agg);
+      int look = L.c - 1;  // chunk index (inside the frame) the window ends at
+      while (true) {
+        const int idx = look - lane;
+        unsigned long long v = VX_FLAG_PREFIX;  // lanes before the frame start act as a zero prefix
+        if (idx >= 0) {
+          do { v = vx_ld_state(st - (L.c - idx)); } while ((v >> 62) == 0);
+        }
+        const unsigned is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int first_p = __ffs(is_prefix) - 1;  // nearest lane holding an inclusive prefix
+        // aggregates of the lanes nearer than the prefix + the prefix itself; all 32 if none yet
+        int contrib = (first_p < 0 || lane <= first_p) ? (int)(unsigned)(v & 0xffffffffull) : 0;
+        if (idx < 0) contrib = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (first_p >= 0) break;  // a prefix (real, or the virtual one before chunk 0) was in the window
+        look -= 32;
+      }
+      if (lane == 0) vx_st_state(st, VX_FLAG_PREFIX | (unsigned)(excl + agg));
+    }
+    if (lane == 0) {
+      s_excl = excl;
+      if (L.c == L.nchunks - 1) {
+        const int total = excl + agg;
+        p.voxel_num[L.f] = total < p.V ? total : p.V;
+      }
+    }
+  }
+  __syncthreads();
   if (flags == 0) return;
-  const int gx = p.grid[0], gy = p.grid[1];
-  const int64_t row0 = p.row_base[L.f];
+  int rank = s_excl + woff + inc - s;
+  int32_t* ccell = p.creator_cell + (L.start - p.pt_lo);
 #pragma unroll
   for (int k = 0; k < VX_ITEMS; ++k) {
     if (!(flags & (1u << k))) continue;
@@ -306,36 +253,19 @@ __global__ void __launch_bounds__(VX_THREADS) vx_assign_kernel(VoxParams p) {
     const int c = cell[k];
     map[c] = ~rank;  // voxel id, stored negative so it never equals a point index
     p.cell[L.start + li - p.pt_lo] = c | VX_CREATOR_BIT;
-    if (rank < p.V) {
-      const int cx = c % gx, cy = (c / gx) % gy, cz = c / (gx * gy);
-      const int64_t row = row0 + rank;
-      if (row < p.capacity) {
-        if (p.coord_cols == 4) {  // batch index first (preprocess.py:44-50)
-          *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(L.f, cz, cy, cx);
-        } else {
-          int32_t* co = p.coords + row * 3;
-          co[0] = cz; co[1] = cy; co[2] = cx;  // reversed (z,y,x), simplevis.py:42
-        }
-      }
-    } else if (rank == p.V && p.overflow == LV_OVERFLOW_BREAK) {
-      p.frame_cut[L.fl] = li;  // simplevis.py:48-49: the loop stops here
-    }
+    ccell[rank] = c;  // rank < number of points of the frame
+    if (rank == p.V && p.overflow == LV_OVERFLOW_BREAK) p.frame_cut[L.fl] = li;  // simplevis.py:48-49
     ++rank;
   }
 }
 
-// ---------------------------------------------------------------- K5: keys + pass-1 histogram
-struct SortPass {
-  int shift, bits;   // digit = (key >> shift) & ((1<<bits)-1)
-  int pass;          // 0: input key0 (indexed by point), 1..: input compacted key/val
-};
-
-__global__ void __launch_bounds__(VX_THREADS) vx_keys_kernel(VoxParams p, SortPass sp) {
+// ---------------------------------------------------------------- K3: keys + bin histogram
+__global__ void __launch_bounds__(VX_THREADS) vx_keys_kernel(VoxParams p) {
   __shared__ int sm[4];
-  __shared__ int hist[VX_MAX_DIGITS];
+  extern __shared__ int hist[];  // [n_bins]
   const ChunkLoc L = vx_locate(p, sm);
   const int32_t* map = p.map + (int64_t)L.fl * p.G;
-  const int D = 1 << sp.bits;
+  const int D = p.n_bins;
   for (int d = threadIdx.x; d < D; d += VX_THREADS) hist[d] = 0;
   __syncthreads();
   const int cut = p.frame_cut[L.fl];
@@ -347,98 +277,110 @@ __global__ void __launch_bounds__(VX_THREADS) vx_keys_kernel(VoxParams p, SortPa
     unsigned key = VX_DROPPED;
     if (li < L.n) {
       const int64_t wi = L.start + li - p.pt_lo;
-      const int cell = p.cell[wi] & ~VX_CREATOR_BIT;
-      if (p.cell[wi] >= 0) {
-        const int vid = ~map[cell];
+      const int craw = p.cell[wi];
+      if (craw >= 0) {
+        const int vid = ~map[craw & ~VX_CREATOR_BIT];
         if (vid < p.V && li < cut) key = (unsigned)vid;
       }
       p.key0[wi] = key;
     }
-    const unsigned digit = key == VX_DROPPED ? 0xffffffffu : ((key >> sp.shift) & (D - 1));
+    const unsigned digit = key == VX_DROPPED ? 0xffffffffu : (key >> p.low_bits);
     const unsigned peers = __match_any_sync(0xffffffffu, digit);
     if (key != VX_DROPPED && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
   }
   __syncthreads();
-  // table layout per frame: [digit][chunk]
   int32_t* tab = p.hist + (int64_t)(__ldg(p.frame_chunk + L.f) - p.chunk_lo) * D;
   for (int d = threadIdx.x; d < D; d += VX_THREADS) tab[(int64_t)d * L.nchunks + L.c] = hist[d];
 }
 
-// histogram of a later pass over the compacted (key,val) list of the frame
-__global__ void __launch_bounds__(VX_THREADS) vx_hist_kernel(VoxParams p, SortPass sp, const uint32_t* __restrict__ keys) {
-  __shared__ int sm[4];
-  __shared__ int hist[VX_MAX_DIGITS];
-  const ChunkLoc L = vx_locate(p, sm);
-  const int D = 1 << sp.bits;
-  for (int d = threadIdx.x; d < D; d += VX_THREADS) hist[d] = 0;
+// ---------------------------------------------------------------- K4: per-frame scan of [bin][chunk]
+// in-place exclusive scan of `n` ints by one CTA; returns the total.
+__device__ int vx_cta_exclusive_scan(int32_t* data, int n, int* sw /*[8]*/, int* carry_sm) {
+  if (threadIdx.x == 0) *carry_sm = 0;
   __syncthreads();
-  const int kept = p.frame_kept[L.fl];
-  const int base = L.c * VX_CHUNK;
-  const int lane = threadIdx.x & 31;
-  if (base < kept) {
-#pragma unroll 2
-    for (int k = 0; k < VX_ITEMS; ++k) {
-      const int li = base + k * VX_THREADS + threadIdx.x;
-      unsigned digit = 0xffffffffu;
-      if (li < kept) digit = (keys[L.start + li - p.pt_lo] >> sp.shift) & (D - 1);
-      const unsigned peers = __match_any_sync(0xffffffffu, digit);
-      if (digit != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += VX_THREADS * 4) {
+    int v[4];
+    int s = 0;
+    const int i0 = base + threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = (i0 + k < n) ? data[i0 + k] : 0;
+      s += v[k];
     }
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) sw[warp] = inc;
+    __syncthreads();
+    int woff = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < VX_WARPS; ++w) {
+      const int t = sw[w];
+      if (w < warp) woff += t;
+      tile_total += t;
+    }
+    int run = *carry_sm + woff + inc - s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < n) data[i0 + k] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *carry_sm += tile_total;
+    __syncthreads();
   }
-  __syncthreads();
-  int32_t* tab = p.hist + (int64_t)(__ldg(p.frame_chunk + L.f) - p.chunk_lo) * D;
-  for (int d = threadIdx.x; d < D; d += VX_THREADS) tab[(int64_t)d * L.nchunks + L.c] = hist[d];
+  return *carry_sm;
 }
 
-// ---------------------------------------------------------------- K6/K9: per-frame scan of [digit][chunk]
-__global__ void __launch_bounds__(VX_THREADS) vx_scan_hist_kernel(VoxParams p, SortPass sp) {
-  __shared__ int sw[VX_THREADS / 32];
+__global__ void __launch_bounds__(VX_THREADS) vx_scan_hist_kernel(VoxParams p) {
+  __shared__ int sw[VX_WARPS];
   __shared__ int carry;
   const int fl = blockIdx.x, f = p.f0 + fl;
-  const int D = 1 << sp.bits;
   const int cb = __ldg(p.frame_chunk + f) - p.chunk_lo;
   const int nch = __ldg(p.frame_chunk + f + 1) - __ldg(p.frame_chunk + f);
-  const int total = vx_cta_exclusive_scan(p.hist + (int64_t)cb * D, nch * D, sw, &carry);
-  if (threadIdx.x == 0) p.frame_kept[fl] = total;
+  const int total = vx_cta_exclusive_scan(p.hist + (int64_t)cb * p.n_bins, nch * p.n_bins, sw, &carry);
+  if (threadIdx.x == 0) {
+    p.frame_kept[fl] = total;
+    if (nch == 0) p.voxel_num[f] = 0;  // a frame without points never ran K2
+  }
 }
 
-// ---------------------------------------------------------------- K7/K10: stable rank + scatter
+// ---------------------------------------------------------------- K5: stable multi-split into bins
 // Warp w owns items [w*256, (w+1)*256) of the chunk in 8 rounds of 32 lanes, so
-// (warp, round, lane) order is point order.  Per-warp digit counters live in shared
-// memory; after the rounds an exclusive scan over the warps (plus the scanned global
-// table) turns them into the warp's base for each digit.
-__global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p, SortPass sp,
-                                                               const uint32_t* __restrict__ keys_in,
-                                                               const int32_t* __restrict__ vals_in,
-                                                               uint32_t* __restrict__ keys_out,
-                                                               int32_t* __restrict__ vals_out) {
+// (warp, round, lane) order is point order.  Per-warp bin counters live in shared memory;
+// after the rounds an exclusive scan over the warps (plus the scanned global table) turns
+// them into the warp's base for each bin.
+__global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p) {
   __shared__ int sm[4];
-  extern __shared__ int cnt[];  // [8][D]
+  extern __shared__ int cnt[];  // [8][n_bins]
   const ChunkLoc L = vx_locate(p, sm);
-  const int D = 1 << sp.bits;
-  const int limit = sp.pass == 0 ? L.n : p.frame_kept[L.fl];
-  const int chunk_base = L.c * VX_CHUNK;
-  if (chunk_base >= limit) return;
+  const int D = p.n_bins;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (VX_THREADS / 32) * D; i += VX_THREADS) cnt[i] = 0;
+  for (int i = threadIdx.x; i < VX_WARPS * D; i += VX_THREADS) cnt[i] = 0;
   __syncthreads();
   int* mycnt = cnt + warp * D;
+  int32_t* map = p.map + (int64_t)L.fl * p.G;
   unsigned key[VX_ITEMS];
-  int val[VX_ITEMS], rnk[VX_ITEMS];
-  const int base = chunk_base + warp * (32 * VX_ITEMS);
+  int rnk[VX_ITEMS];
+  const int base = L.c * VX_CHUNK + warp * (32 * VX_ITEMS);
   const unsigned lt = lv_lanemask_lt();
 #pragma unroll
   for (int r = 0; r < VX_ITEMS; ++r) {
     const int li = base + r * 32 + lane;
     key[r] = VX_DROPPED;
-    val[r] = 0;
-    if (li < limit) {
+    if (li < L.n) {
       const int64_t wi = L.start + li - p.pt_lo;
-      key[r] = keys_in[wi];
-      val[r] = sp.pass == 0 ? li : vals_in[wi];
+      key[r] = p.key0[wi];
+      const int craw = p.cell[wi];
+      // touched-cell reset: K3 was the last reader of first[]
+      if (craw >= 0 && (craw & VX_CREATOR_BIT)) map[craw & ~VX_CREATOR_BIT] = VX_EMPTY;
     }
     const bool live = key[r] != VX_DROPPED;
-    const unsigned digit = live ? ((key[r] >> sp.shift) & (D - 1)) : 0xffffffffu;
+    const unsigned digit = live ? (key[r] >> p.low_bits) : 0xffffffffu;
     const unsigned peers = __match_any_sync(0xffffffffu, digit);
     int old = 0;
     const int leader = __ffs(peers) - 1;
@@ -451,140 +393,227 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p, Sor
     __syncwarp();
   }
   __syncthreads();
-  // warp bases: global table entry (already exclusive-scanned) + counts of the lower warps
   const int32_t* tab = p.hist + (int64_t)(__ldg(p.frame_chunk + L.f) - p.chunk_lo) * D;
   for (int d = threadIdx.x; d < D; d += VX_THREADS) {
     int off = tab[(int64_t)d * L.nchunks + L.c];
 #pragma unroll
-    for (int w = 0; w < VX_THREADS / 32; ++w) {
+    for (int w = 0; w < VX_WARPS; ++w) {
       const int t = cnt[w * D + d];
       cnt[w * D + d] = off;
       off += t;
     }
   }
   __syncthreads();
-  const int64_t out0 = L.start - p.pt_lo;  // the frame's sorted list starts at its first point slot
+  const int64_t out0 = L.start - p.pt_lo;  // the frame's list starts at its first point slot
 #pragma unroll
   for (int r = 0; r < VX_ITEMS; ++r) {
     if (key[r] == VX_DROPPED) continue;
-    const unsigned digit = (key[r] >> sp.shift) & (D - 1);
-    const int64_t pos = out0 + mycnt[digit] + rnk[r];
-    keys_out[pos] = key[r];
-    vals_out[pos] = val[r];
+    const int64_t pos = out0 + mycnt[key[r] >> p.low_bits] + rnk[r];
+    p.keys[pos] = key[r];
+    p.vals[pos] = base + r * 32 + lane;
   }
 }
 
-// ---------------------------------------------------------------- K11: voxel segments
-__global__ void __launch_bounds__(VX_THREADS) vx_heads_kernel(VoxParams p, const uint32_t* __restrict__ keys) {
-  __shared__ int sm[4];
-  const ChunkLoc L = vx_locate(p, sm);
-  const int kept = p.frame_kept[L.fl];
-  const int base = L.c * VX_CHUNK;
-  if (base >= kept) return;
-  const uint32_t* k = keys + (L.start - p.pt_lo);
-  int32_t* ss = p.seg_start + (int64_t)L.fl * p.V;
-  int32_t* se = p.seg_end + (int64_t)L.fl * p.V;
-#pragma unroll 2
-  for (int j = 0; j < VX_ITEMS; ++j) {
-    const int li = base + j * VX_THREADS + threadIdx.x;
-    if (li >= kept) continue;
-    const unsigned me = k[li];
-    if (li == 0 || k[li - 1] != me) ss[me] = li;
-    if (li == kept - 1 || k[li + 1] != me) se[me] = li + 1;
-  }
-}
+// ---------------------------------------------------------------- K6: bins -> output rows
+// grid = (n_bins, frames).  Shared memory: slot table [2^L][T] of point indices, running
+// per-voxel counts [2^L], per-warp tile counters [8][2^L], (fused) decoration stage.
+template <bool DECO, bool C4>
+__global__ void __launch_bounds__(VX_THREADS, 4) vx_bins_kernel(VoxParams p, DecoCfg d, float* __restrict__ decorated) {
+  extern __shared__ __align__(16) int smem[];
+  const int NV = 1 << p.low_bits;
+  int* slot_tab = smem;                    // [NV][T]
+  int* total = slot_tab + NV * p.T;        // [NV]
+  int* wcnt = total + NV;                  // [8][NV]
+  float* stage = reinterpret_cast<float*>(wcnt + VX_WARPS * NV);  // [8][T*C_out] (DECO only)
+  __shared__ long long s_row0;
 
-// ---------------------------------------------------------------- K12: gather into voxels
-// LPV lanes cooperate on one voxel (32 for pillars, 8 for T=5).  grid = (GX, frames); the
-// voxel groups of a CTA loop over the frame's voxels, so no CTA is launched for rows that
-// do not exist (voxel_num is only known on the device).
-template <int LPV, bool C4>
-__global__ void __launch_bounds__(VX_THREADS) vx_gather_kernel(VoxParams p, const int32_t* __restrict__ vals) {
-  const int fl = blockIdx.y, f = p.f0 + fl;
-  const int sub = threadIdx.x % LPV;
+  const int fl = blockIdx.y, f = p.f0 + fl, b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int vnum = p.voxel_num[f];
-  const int limit = (p.zero_tail && !p.concat) ? p.V : vnum;
-  const int64_t row0 = p.row_base[f];
-  const int64_t fstart = __ldg(p.frame_off + f);
-  const int groups = VX_THREADS / LPV;
-  for (int v = blockIdx.x * groups + threadIdx.x / LPV; v < limit; v += gridDim.x * groups) {
-    const int64_t row = row0 + v;
-    if (row >= p.capacity) break;
-    float* out = p.voxels + row * p.T * p.C;
-    int n = 0;
-    int s = 0;
-    if (v < vnum) {
-      s = p.seg_start[(int64_t)fl * p.V + v];
-      n = p.seg_end[(int64_t)fl * p.V + v] - s;
-      if (n > p.T) n = p.T;
-    }
-    if (sub == 0) {
-      p.num_points[row] = n;
-      if (v >= vnum) {
-        int32_t* co = p.coords + row * p.coord_cols;
-        for (int j = 0; j < p.coord_cols; ++j) co[j] = 0;
-      }
-    }
-    const int32_t* vv = vals + (fstart - p.pt_lo) + s;
-    if (C4) {
-      float4* o4 = reinterpret_cast<float4*>(out);
-      for (int t = sub; t < p.T; t += LPV) {
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t < n) q = __ldg(reinterpret_cast<const float4*>(p.pts) + fstart + vv[t]);
-        lv_st_stream_f4(o4 + t, q);
-      }
-    } else {
-      for (int t = sub; t < p.T; t += LPV) {
-        const float* src = (t < n) ? p.pts + (fstart + vv[t]) * p.C : nullptr;
-        for (int c = 0; c < p.C; ++c) out[t * p.C + c] = src ? __ldg(src + c) : 0.f;
-      }
-    }
-  }
-}
-
-// K12': gather fused with the PillarFeatureNet decoration (pointpillars.py:203-231): the
-// (P,T,4) voxel tensor is never written; one warp per pillar pulls its <= T points through
-// the sorted index list straight into registers and emits the decorated (T,C_out) block.
-__global__ void __launch_bounds__(VX_THREADS, 6) vx_gather_decorate_kernel(VoxParams p, const int32_t* __restrict__ vals,
-                                                                          DecoCfg d, float* __restrict__ decorated) {
-  extern __shared__ float stage[];  // [8 warps][T*C_out]
-  const int fl = blockIdx.y, f = p.f0 + fl;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int vnum = p.voxel_num[f];
-  const int64_t row0 = p.row_base[f];
-  const int64_t fstart = __ldg(p.frame_off + f);
-  const int per = d.T * d.C_out;
-  float* st = stage + warp * per;
-  const float4* pts4 = reinterpret_cast<const float4*>(p.pts) + fstart;
-  for (int v = blockIdx.x * (VX_THREADS / 32) + warp; v < vnum; v += gridDim.x * (VX_THREADS / 32)) {
-    const int64_t row = row0 + v;
-    if (row >= p.capacity) break;
-    const int s = p.seg_start[(int64_t)fl * p.V + v];
-    int n = p.seg_end[(int64_t)fl * p.V + v] - s;
-    if (n > d.T) n = d.T;
-    const int32_t* vv = vals + (fstart - p.pt_lo) + s;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (lane < n) a = __ldg(pts4 + vv[lane]);
-    if (lane + 32 < n) b = __ldg(pts4 + vv[lane + 32]);
-    const int4 co = *reinterpret_cast<const int4*>(p.coords + row * 4);  // b, z, y, x (written by K4)
-    if (lane == 0) p.num_points[row] = n;
-    lv_decorate_warp(a, b, n, co.z, co.w, d, st, decorated + row * per, lane);
-  }
-}
-
-// ---------------------------------------------------------------- K13: touched-cell reset
-__global__ void __launch_bounds__(VX_THREADS) vx_reset_kernel(VoxParams p) {
-  __shared__ int sm[4];
-  const ChunkLoc L = vx_locate(p, sm);
-  int32_t* map = p.map + (int64_t)L.fl * p.G;
-  const int base = L.c * VX_CHUNK;
+  if ((b << p.low_bits) >= vnum && b != 0) return;  // bin beyond the last voxel: nothing to do
+  // first output row of the frame: prefix of voxel_num over the earlier frames of the batch
+  if (warp == 0) {
+    long long rb;
+    if (p.concat) {
+      int acc = 0;
+      for (int g = p.f0 + lane; g < f; g += 32) acc += p.voxel_num[g];
 #pragma unroll
-  for (int k = 0; k < VX_ITEMS; ++k) {
-    const int li = base + k * VX_THREADS + threadIdx.x;
-    if (li < L.n) {
-      const int c = p.cell[L.start + li - p.pt_lo];
-      if (c >= 0 && (c & VX_CREATOR_BIT)) map[c & ~VX_CREATOR_BIT] = VX_EMPTY;
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      rb = p.row_base[p.f0] + acc;
+    } else {
+      rb = (long long)f * p.V;
     }
+    if (lane == 0) {
+      s_row0 = rb;
+      if (b == 0 && p.concat) {
+        if (f > p.f0) p.row_base[f] = rb;
+        if (f + 1 == p.f1) p.row_base[f + 1] = rb + vnum;
+      }
+    }
+  }
+  const int v0 = b << p.low_bits;
+  int nv = vnum - v0;
+  if (nv > NV) nv = NV;
+  const int cb = __ldg(p.frame_chunk + f) - p.chunk_lo;
+  const int nch = __ldg(p.frame_chunk + f + 1) - __ldg(p.frame_chunk + f);
+  if (nv <= 0 || nch == 0) return;  // (uniform across the CTA)
+  const int32_t* tab = p.hist + (int64_t)cb * p.n_bins;
+  const int seg_lo = tab[(int64_t)b * nch];
+  const int seg_hi = (b + 1 < p.n_bins) ? tab[(int64_t)(b + 1) * nch] : p.frame_kept[fl];
+  const int64_t fstart = __ldg(p.frame_off + f);
+  const uint32_t* keys = p.keys + (fstart - p.pt_lo);
+  const int32_t* vals = p.vals + (fstart - p.pt_lo);
+
+  for (int i = threadIdx.x; i < NV; i += VX_THREADS) total[i] = 0;
+  const unsigned lt = lv_lanemask_lt();
+  const unsigned lowmask = NV - 1;
+  // ---- phase 1: stable rank by voxel inside the bin, tile by tile (2048 points) ----
+  for (int tile0 = seg_lo; tile0 < seg_hi; tile0 += VX_CHUNK) {
+    for (int i = threadIdx.x; i < VX_WARPS * NV; i += VX_THREADS) wcnt[i] = 0;
+    __syncthreads();
+    int* mycnt = wcnt + warp * NV;
+    unsigned dig[VX_ITEMS];
+    int val[VX_ITEMS], rnk[VX_ITEMS];
+    // every warp owns a contiguous span of the tile (point order = warp, round, lane); the
+    // span shrinks with the tile so that small bins still keep all 8 warps busy
+    int n_tile = seg_hi - tile0;
+    if (n_tile > VX_CHUNK) n_tile = VX_CHUNK;
+    const int span = (((n_tile + VX_WARPS - 1) / VX_WARPS) + 31) & ~31;
+    const int rounds = span >> 5;
+    const int base = tile0 + warp * span;
+    const int tile_hi = tile0 + n_tile;
+#pragma unroll
+    for (int r = 0; r < VX_ITEMS; ++r) {
+      dig[r] = 0xffffffffu;
+      val[r] = 0;
+      rnk[r] = 0;
+      if (r >= rounds) continue;  // warp-uniform
+      const int pos = base + r * 32 + lane;
+      if (pos < tile_hi) {
+        dig[r] = keys[pos] & lowmask;
+        val[r] = vals[pos];
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, dig[r]);
+      const int leader = __ffs(peers) - 1;
+      int old = 0;
+      if (dig[r] != 0xffffffffu && lane == leader) {
+        old = mycnt[dig[r]];
+        mycnt[dig[r]] = old + __popc(peers);
+      }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      rnk[r] = old + __popc(peers & lt);
+      __syncwarp();
+    }
+    __syncthreads();
+    // warp bases = running per-voxel total + counts of the lower warps; totals advance
+    for (int v = threadIdx.x; v < NV; v += VX_THREADS) {
+      int off = total[v];
+#pragma unroll
+      for (int w = 0; w < VX_WARPS; ++w) {
+        const int t = wcnt[w * NV + v];
+        wcnt[w * NV + v] = off;
+        off += t;
+      }
+      total[v] = off;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < VX_ITEMS; ++r) {
+      if (dig[r] == 0xffffffffu) continue;
+      const int slot = mycnt[dig[r]] + rnk[r];
+      if (slot < p.T) slot_tab[dig[r] * p.T + slot] = val[r];  // first T points in point order
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  // ---- phase 2: one (sub)warp per voxel writes the output row ----
+  const long long row0 = s_row0;
+  const int32_t* ccell = p.creator_cell + (fstart - p.pt_lo);
+  const int gx = p.grid[0], gy = p.grid[1];
+  if (DECO) {
+    const int per = d.T * d.C_out;
+    float* st = stage + warp * per;
+    const float4* pts4 = reinterpret_cast<const float4*>(p.pts) + fstart;
+    // two pillars per iteration: the point gathers of both are in flight before either is used
+    for (int v = warp * 2; v < nv; v += VX_WARPS * 2) {
+      const long long row = row0 + v0 + v;
+      if (row >= p.capacity) break;
+      const bool two = (v + 1 < nv) && (row + 1 < p.capacity);
+      int n0 = total[v], n1 = two ? total[v + 1] : 0;
+      if (n0 > p.T) n0 = p.T;
+      if (n1 > p.T) n1 = p.T;
+      const int* sl = slot_tab + v * p.T;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 a0 = z4, b0 = z4, a1 = z4, b1 = z4;
+      if (lane < n0) a0 = __ldg(pts4 + sl[lane]);
+      if (lane + 32 < n0) b0 = __ldg(pts4 + sl[lane + 32]);
+      if (lane < n1) a1 = __ldg(pts4 + sl[p.T + lane]);
+      if (lane + 32 < n1) b1 = __ldg(pts4 + sl[p.T + lane + 32]);
+      const int c0 = ccell[v0 + v], c1 = two ? ccell[v0 + v + 1] : 0;
+      const int cx0 = c0 % gx, cy0 = (c0 / gx) % gy, cz0 = c0 / (gx * gy);
+      const int cx1 = c1 % gx, cy1 = (c1 / gx) % gy, cz1 = c1 / (gx * gy);
+      if (lane == 0) {
+        p.num_points[row] = n0;
+        *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(f, cz0, cy0, cx0);  // preprocess.py:44-50
+        if (two) {
+          p.num_points[row + 1] = n1;
+          *reinterpret_cast<int4*>(p.coords + (row + 1) * 4) = make_int4(f, cz1, cy1, cx1);
+        }
+      }
+      lv_decorate_warp(a0, b0, n0, cy0, cx0, d, st, decorated + row * per, lane);
+      if (two) lv_decorate_warp(a1, b1, n1, cy1, cx1, d, st, decorated + (row + 1) * per, lane);
+    }
+  } else {
+    // LPV lanes per voxel: 32 for pillars, 8 for T <= 8
+    const int LPV = p.T > 16 ? 32 : (p.T > 8 ? 16 : 8);
+    const int groups = VX_THREADS / LPV;
+    const int sub = threadIdx.x % LPV;
+    for (int v = threadIdx.x / LPV; v < nv; v += groups) {
+      const long long row = row0 + v0 + v;
+      if (row >= p.capacity) break;
+      int n = total[v];
+      if (n > p.T) n = p.T;
+      const int* sl = slot_tab + v * p.T;
+      if (sub == 0) {
+        p.num_points[row] = n;
+        const int c = ccell[v0 + v];
+        const int cx = c % gx, cy = (c / gx) % gy, cz = c / (gx * gy);
+        if (p.coord_cols == 4) {
+          *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(f, cz, cy, cx);
+        } else {
+          int32_t* co = p.coords + row * 3;
+          co[0] = cz; co[1] = cy; co[2] = cx;  // reversed (z,y,x), simplevis.py:42
+        }
+      }
+      float* out = p.voxels + row * p.T * p.C;
+      if (C4) {
+        float4* o4 = reinterpret_cast<float4*>(out);
+        for (int t = sub; t < p.T; t += LPV) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t < n) q = __ldg(reinterpret_cast<const float4*>(p.pts) + fstart + sl[t]);
+          lv_st_stream_f4(o4 + t, q);
+        }
+      } else {
+        for (int t = sub; t < p.T; t += LPV) {
+          const float* src = (t < n) ? p.pts + (fstart + sl[t]) * p.C : nullptr;
+          for (int cc = 0; cc < p.C; ++cc) out[t * p.C + cc] = src ? __ldg(src + cc) : 0.f;
+        }
+      }
+    }
+  }
+}
+
+// rows [voxel_num, V) of the padded layout (generate_multi_gpu, preprocess.py:311-317)
+__global__ void __launch_bounds__(VX_THREADS) vx_zero_tail_kernel(VoxParams p) {
+  const int f = p.f0 + blockIdx.y;
+  const int vnum = p.voxel_num[f];
+  const int per = p.T * p.C;
+  for (int v = vnum + blockIdx.x; v < p.V; v += gridDim.x) {
+    const int64_t row = (int64_t)f * p.V + v;
+    float* out = p.voxels + row * per;
+    for (int i = threadIdx.x; i < per; i += VX_THREADS) out[i] = 0.f;
+    if (threadIdx.x < 3) p.coords[row * 3 + threadIdx.x] = 0;
+    if (threadIdx.x == 3) p.num_points[row] = 0;
   }
 }
 
@@ -600,10 +629,11 @@ extern "C" int lv_voxel_grid_size(const lv_voxel_config* cfg, int32_t grid_xyz[3
   return LV_OK;
 }
 
-static int vx_bits_for(int v) {  // bits needed for ids in [0, v)
-  int b = 1;
-  while ((1ll << b) < v) ++b;
-  return b;
+template <typename K>
+static int vx_set_smem(K kernel, size_t bytes) {
+  if (bytes > 40 * 1024)  // dynamic + the kernels' few static bytes must stay under the 48 KB default
+    LV_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return LV_OK;
 }
 
 static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
@@ -631,7 +661,20 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
              "lv_pillarize_concat: needs 4 features per point, max_points <= 64 and 16-byte aligned points");
   const int V = cfg->max_voxels, T = cfg->max_points, C = cfg->num_features;
 
-  // chunk prefix per frame (a frame with no points still owns zero chunks)
+  // bins: 2^L voxel ids each, L as large as a 32 KB slot table allows
+  int L = VX_MAX_LOW_BITS;
+  while (L > 0 && ((size_t)1 << L) * T * 4 > 32 * 1024) --L;
+  while ((((int64_t)V + (1 << L) - 1) >> L) > VX_MAX_BINS && L < 20) ++L;
+  const int n_bins = (int)(((int64_t)V + (1 << L) - 1) >> L);
+  const int NV = 1 << L;
+  const size_t deco_stage = deco ? (size_t)VX_WARPS * T * deco->C_out * 4 : 0;
+  const size_t smem_bins = ((size_t)NV * T + NV + (size_t)VX_WARPS * NV) * 4 + deco_stage;
+  LV_REQUIRE(smem_bins <= 220 * 1024, "lv_voxelize: max_points %d x max_voxels %d needs %zu bytes of shared memory "
+             "per bin (limit 220 KB)", T, V, smem_bins);
+  const size_t smem_scatter = (size_t)VX_WARPS * n_bins * 4;
+  const size_t smem_keys = (size_t)n_bins * 4;
+
+  // chunk prefix per frame (a frame with no points owns zero chunks)
   std::vector<int32_t> frame_chunk(n_frames + 1, 0);
   for (int f = 0; f < n_frames; ++f) {
     const int64_t n = h_frame_offsets[f + 1] - h_frame_offsets[f];
@@ -650,17 +693,16 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   LV_CHECK(h->vox_frame_offsets.sync(h_frame_offsets, sizeof(int64_t) * (n_frames + 1), stream, &d_off));
   LV_CHECK(h->vox_chunk_table.sync(frame_chunk.data(), sizeof(int32_t) * (n_frames + 1), stream, &d_chunk));
 
-  // sub-batches: bounded by the dense map budget and by the point workspace
-  const int64_t map_budget = h->vox_dense_map_limit_bytes > 0 ? h->vox_dense_map_limit_bytes : (64ll << 20);
+  // sub-batches: bounded by the dense map budget (L2 residency) and by the point workspace,
+  // then balanced so that no launch is a small remainder
+  // 96 MB of the 126 MB L2 measured best (bench.py: 64 MB 0.94 ms, 96 MB 0.90 ms, 128 MB 0.88 ms per
+  // 128 pillar frames); beyond the L2 the random atomicMin traffic would go to HBM
+  const int64_t map_budget = h->vox_dense_map_limit_bytes > 0 ? h->vox_dense_map_limit_bytes : (96ll << 20);
   int64_t fif = map_budget / (G * 4);
   if (fif < 1) fif = 1;
   if (fif > n_frames) fif = n_frames;
+  fif = lv_div_up(n_frames, lv_div_up(n_frames, fif));
   const int64_t max_pts = 8ll << 20;
-
-  const int bits = vx_bits_for(V);
-  const int npass = (bits + VX_MAX_DIGIT_BITS - 1) / VX_MAX_DIGIT_BITS;
-  const int dbits = (bits + npass - 1) / npass;
-  const int D = 1 << dbits;
 
   VoxParams p;
   memset(&p, 0, sizeof(p));
@@ -673,6 +715,7 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     p.grid[j] = grid[j];
   }
   p.G = G; p.T = T; p.V = V; p.overflow = cfg->overflow_mode; p.zero_tail = cfg->zero_tail;
+  p.low_bits = L; p.n_bins = n_bins;
   p.voxels = d_voxels; p.coords = d_coords; p.num_points = d_num_points; p.voxel_num = d_voxel_num;
   p.concat = concat;
   p.coord_cols = concat ? 4 : 3;
@@ -688,6 +731,15 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   }
   const bool c4 = (C == 4) && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0;
   const bool out4 = c4 && (reinterpret_cast<uintptr_t>(d_voxels) & 15) == 0;
+  DecoCfg dcfg;
+  memset(&dcfg, 0, sizeof(dcfg));
+  if (deco) dcfg = *deco;
+
+  LV_CHECK(vx_set_smem(vx_keys_kernel, smem_keys));
+  LV_CHECK(vx_set_smem(vx_scatter_kernel, smem_scatter));
+  if (deco) LV_CHECK(vx_set_smem(vx_bins_kernel<true, true>, smem_bins));
+  else if (out4) LV_CHECK(vx_set_smem(vx_bins_kernel<false, true>, smem_bins));
+  else LV_CHECK(vx_set_smem(vx_bins_kernel<false, false>, smem_bins));
 
   int f0 = 0;
   while (f0 < n_frames) {
@@ -701,90 +753,48 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     LV_CHECK(h->vox_map.ensure((size_t)nf * G * 4, stream, 0x7f));
     LV_CHECK(h->vox_cell.ensure((size_t)(npts + 1) * 4 * 2, stream));            // cell + key0
     LV_CHECK(h->vox_keys[0].ensure((size_t)(npts + 1) * 4, stream));
-    LV_CHECK(h->vox_keys[1].ensure((size_t)(npts + 1) * 4, stream));
     LV_CHECK(h->vox_vals[0].ensure((size_t)(npts + 1) * 4, stream));
-    LV_CHECK(h->vox_vals[1].ensure((size_t)(npts + 1) * 4, stream));
-    LV_CHECK(h->vox_chunk.ensure((size_t)(nchunks + 1) * 4, stream));
-    LV_CHECK(h->vox_hist.ensure((size_t)(nchunks + 1) * D * 4, stream));
-    LV_CHECK(h->vox_frame_state.ensure((size_t)nf * (3 + 2 * (size_t)V) * 4, stream));
+    LV_CHECK(h->vox_aux.ensure((size_t)(npts + 1) * 4, stream));                 // creator_cell
+    LV_CHECK(h->vox_chunk.ensure((size_t)(nchunks + 1) * 8, stream));            // look-back descriptors
+    LV_CHECK(h->vox_hist.ensure((size_t)(nchunks + 1) * n_bins * 4, stream));
+    LV_CHECK(h->vox_frame_state.ensure((size_t)nf * 2 * 4, stream));
     p.map = h->vox_map.as<int32_t>();
     p.cell = h->vox_cell.as<int32_t>();
     p.key0 = h->vox_cell.as<uint32_t>() + (npts + 1);
-    p.keyA = h->vox_keys[0].as<uint32_t>(); p.valA = h->vox_vals[0].as<int32_t>();
-    p.keyB = h->vox_keys[1].as<uint32_t>(); p.valB = h->vox_vals[1].as<int32_t>();
-    p.chunk_cnt = h->vox_chunk.as<int32_t>();
+    p.keys = h->vox_keys[0].as<uint32_t>();
+    p.vals = h->vox_vals[0].as<int32_t>();
+    p.creator_cell = h->vox_aux.as<int32_t>();
+    p.chunk_state = h->vox_chunk.as<unsigned long long>();
     p.hist = h->vox_hist.as<int32_t>();
-    int32_t* fs = h->vox_frame_state.as<int32_t>();
-    p.frame_total = fs; p.frame_cut = fs + nf; p.frame_kept = fs + 2 * nf;
-    p.seg_start = fs + 3 * nf; p.seg_end = p.seg_start + (size_t)nf * V;
+    p.frame_cut = h->vox_frame_state.as<int32_t>();
+    p.frame_kept = p.frame_cut + nf;
 
     if (nchunks > 0) {
       if (c4) vx_cells_kernel<true><<<nchunks, VX_THREADS, 0, stream>>>(p);
       else vx_cells_kernel<false><<<nchunks, VX_THREADS, 0, stream>>>(p);
       LV_LAUNCH_CHECK(h);
-      vx_count_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p);
-      LV_LAUNCH_CHECK(h);
-    }
-    vx_scan_chunks_kernel<<<nf, VX_THREADS, 0, stream>>>(p);
-    LV_LAUNCH_CHECK(h);
-    if (concat) {
-      vx_row_base_kernel<<<1, 32, 0, stream>>>(p);
-      LV_LAUNCH_CHECK(h);
-    }
-    const uint32_t* sorted_keys = p.keyA;
-    const int32_t* sorted_vals = p.valA;
-    if (nchunks > 0) {
       vx_assign_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p);
       LV_LAUNCH_CHECK(h);
-      const size_t smem = (size_t)(VX_THREADS / 32) * D * sizeof(int);
-      for (int pass = 0; pass < npass; ++pass) {
-        SortPass sp{pass * dbits, dbits, pass};
-        const uint32_t* kin = pass == 0 ? p.key0 : ((pass & 1) ? p.keyA : p.keyB);
-        const int32_t* vin = (pass & 1) ? p.valA : p.valB;
-        uint32_t* kout = (pass & 1) ? p.keyB : p.keyA;
-        int32_t* vout = (pass & 1) ? p.valB : p.valA;
-        if (pass == 0) vx_keys_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p, sp);
-        else vx_hist_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p, sp, kin);
-        LV_LAUNCH_CHECK(h);
-        vx_scan_hist_kernel<<<nf, VX_THREADS, 0, stream>>>(p, sp);
-        LV_LAUNCH_CHECK(h);
-        vx_scatter_kernel<<<nchunks, VX_THREADS, smem, stream>>>(p, sp, kin, vin, kout, vout);
-        LV_LAUNCH_CHECK(h);
-        sorted_keys = kout;
-        sorted_vals = vout;
-      }
-      vx_heads_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p, sorted_keys);
+      vx_keys_kernel<<<nchunks, VX_THREADS, smem_keys, stream>>>(p);
       LV_LAUNCH_CHECK(h);
     }
-    if (deco) {
-      const size_t smem = (size_t)(VX_THREADS / 32) * T * deco->C_out * sizeof(float);
-      if (smem > 48 * 1024)
-        LV_CHECK_CUDA(cudaFuncSetAttribute(vx_gather_decorate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int gx = (int)lv_div_up((int64_t)h->num_sms * 12, nf);
-      if (gx < 8) gx = 8;
-      dim3 grid_g((unsigned)gx, (unsigned)nf);
-      vx_gather_decorate_kernel<<<grid_g, VX_THREADS, smem, stream>>>(p, sorted_vals, *deco, d_decorated);
-      LV_LAUNCH_CHECK(h);
-    } else {
-      const int lpv = T >= 24 ? 32 : (T >= 12 ? 16 : 8);
-      const int64_t full = lv_div_up((int64_t)V * lpv, VX_THREADS);
-      int64_t gx = lv_div_up((int64_t)h->num_sms * 16, nf);
-      if (gx < 8) gx = 8;
-      if (gx > full) gx = full;
-      dim3 grid_g((unsigned)gx, (unsigned)nf);
-      if (out4) {
-        if (lpv == 32) vx_gather_kernel<32, true><<<grid_g, VX_THREADS, 0, stream>>>(p, sorted_vals);
-        else if (lpv == 16) vx_gather_kernel<16, true><<<grid_g, VX_THREADS, 0, stream>>>(p, sorted_vals);
-        else vx_gather_kernel<8, true><<<grid_g, VX_THREADS, 0, stream>>>(p, sorted_vals);
-      } else {
-        if (lpv == 32) vx_gather_kernel<32, false><<<grid_g, VX_THREADS, 0, stream>>>(p, sorted_vals);
-        else if (lpv == 16) vx_gather_kernel<16, false><<<grid_g, VX_THREADS, 0, stream>>>(p, sorted_vals);
-        else vx_gather_kernel<8, false><<<grid_g, VX_THREADS, 0, stream>>>(p, sorted_vals);
-      }
-      LV_LAUNCH_CHECK(h);
-    }
+    vx_scan_hist_kernel<<<nf, VX_THREADS, 0, stream>>>(p);
+    LV_LAUNCH_CHECK(h);
     if (nchunks > 0) {
-      vx_reset_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p);
+      vx_scatter_kernel<<<nchunks, VX_THREADS, smem_scatter, stream>>>(p);
+      LV_LAUNCH_CHECK(h);
+    }
+    {
+      dim3 grid_b((unsigned)n_bins, (unsigned)nf);
+      if (deco) vx_bins_kernel<true, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, d_decorated);
+      else if (out4) vx_bins_kernel<false, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, nullptr);
+      else vx_bins_kernel<false, false><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, nullptr);
+      LV_LAUNCH_CHECK(h);
+    }
+    if (!concat && cfg->zero_tail) {
+      int gx = (int)lv_div_up((int64_t)h->num_sms * 8, nf);
+      if (gx > V) gx = V;
+      vx_zero_tail_kernel<<<dim3((unsigned)gx, (unsigned)nf), VX_THREADS, 0, stream>>>(p);
       LV_LAUNCH_CHECK(h);
     }
     f0 = f1;

@@ -38,6 +38,11 @@ class FrameBatchEngine:
         self.lib = nat.load()
         self.dev = torch.device("cuda", device)
         self.h = nat.get_handle(device)
+        import os as _os
+        if _os.environ.get("LV_VOX_MAP_MB"):
+            self.h.set_option("vox_dense_map_limit_bytes", int(_os.environ["LV_VOX_MAP_MB"]) << 20)
+        if _os.environ.get("LV_BEV_FIF"):
+            self.h.set_option("bev_frames_in_flight", int(_os.environ["LV_BEV_FIF"]))
         self.F = int(frames_per_step)
         self.n = int(points_per_frame)
         self.bev_shape = tuple(int(s) for s in bev_shape)
