@@ -28,13 +28,9 @@ __device__ __forceinline__ float lv_warp_min(float v) {
   return v;
 }
 
-// one slot of one pillar -> C_out floats at o (C == 4 input features)
-__device__ __forceinline__ void lv_decorate_slot(const float4 q, bool live, float mx, float my, float mz, float cx,
-                                                 float cy, float height, const DecoCfg& d, float* o) {
-  if (!live) {  // padding mask (:226-231)
-    for (int c = 0; c < d.C_out; ++c) o[c] = 0.f;
-    return;
-  }
+// one LIVE slot of one pillar -> C_out floats at o (C == 4 input features)
+__device__ __forceinline__ void lv_decorate_slot(const float4 q, float mx, float my, float mz, float cx, float cy,
+                                                 float height, const DecoCfg& d, float* o) {
   const float x = q.x, y = q.y, z = q.z;
   const float px = x - cx, py = y - cy;  // f_center (:213-217)
   int k = 0;
@@ -59,10 +55,30 @@ __device__ __forceinline__ void lv_decorate_slot(const float4 q, bool live, floa
   }
 }
 
-// Decorates one pillar (T <= 64, C == 4) held in registers by one warp: lane owns slot
-// `lane` (a) and slot `lane + 32` (b); slots >= T must be passed as zeros.  The result,
-// T*C_out floats laid out [t][C_out], is staged in the warp's shared-memory region `st`
-// and then written to `dst` with contiguous (128-bit when aligned) stores.
+// An output row is [num*C_out floats of data][zeros] (padding mask, :226-231): most of a
+// pillar is padding (5.4 of 60 slots are live on a Lyft sweep), so the zero part is stored
+// straight from registers - it depends on nothing but `num` and is issued BEFORE the point
+// gathers are consumed - and only the live slots go through the shared-memory stage.
+__device__ __forceinline__ bool lv_row_vec4(const DecoCfg& d, const float* dst) {
+  return ((d.T * d.C_out) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+}
+__device__ __forceinline__ int lv_live_slots(int num, const DecoCfg& d) { return num < 0 ? 0 : (num > d.T ? d.T : num); }
+__device__ __forceinline__ void lv_decorate_zero_tail(int num, const DecoCfg& d, float* __restrict__ dst, int lane) {
+  const int per = d.T * d.C_out, nd = lv_live_slots(num, d) * d.C_out;
+  if (lv_row_vec4(d, dst)) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = ((nd + 3) >> 2) + lane; j < (per >> 2); j += 32) lv_st_stream_f4(d4 + j, z4);
+  } else {
+    for (int i = nd + lane; i < per; i += 32) dst[i] = 0.f;
+  }
+}
+
+// Decorates the live part of one pillar (T <= 64, C == 4) held in registers by one warp:
+// lane owns slot `lane` (a) and slot `lane + 32` (b); slots >= num must be passed as zeros.
+// The num*C_out floats, laid out [t][C_out], are staged in the warp's shared-memory region
+// `st` and written to `dst` with contiguous (128-bit when aligned) stores.  The caller has
+// already issued lv_decorate_zero_tail for the rest of the row.
 __device__ __forceinline__ void lv_decorate_warp(const float4 a, const float4 b, int num, int coor_y, int coor_x,
                                                  const DecoCfg& d, float* st, float* __restrict__ dst, int lane) {
   // mean over ALL T slots, padding zeros included (:208-209)
@@ -79,16 +95,20 @@ __device__ __forceinline__ void lv_decorate_warp(const float4 a, const float4 b,
   // pillar centre: coors*vx + x_offset as a separate multiply and add (:213-217)
   const float cx = __fadd_rn(__fmul_rn((float)coor_x, d.vx), d.x_off);
   const float cy = __fadd_rn(__fmul_rn((float)coor_y, d.vy), d.y_off);
-  if (lane < d.T) lv_decorate_slot(a, lane < num, mx, my, mz, cx, cy, height, d, st + lane * d.C_out);
-  if (lane + 32 < d.T) lv_decorate_slot(b, lane + 32 < num, mx, my, mz, cx, cy, height, d, st + (lane + 32) * d.C_out);
-  __syncwarp();
-  const int per = d.T * d.C_out;
-  if ((per & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+  const int live = lv_live_slots(num, d);
+  if (lane < live) lv_decorate_slot(a, mx, my, mz, cx, cy, height, d, st + lane * d.C_out);
+  if (lane + 32 < live) lv_decorate_slot(b, mx, my, mz, cx, cy, height, d, st + (lane + 32) * d.C_out);
+  const int nd = live * d.C_out;
+  if (lv_row_vec4(d, dst)) {
+    const int nd4 = (nd + 3) >> 2;
+    if (lane < (nd4 << 2) - nd) st[nd + lane] = 0.f;  // pad the last quad of the data part
+    __syncwarp();
     const float4* s4 = reinterpret_cast<const float4*>(st);
     float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int i = lane; i < per / 4; i += 32) lv_st_stream_f4(d4 + i, s4[i]);
+    for (int i = lane; i < nd4; i += 32) lv_st_stream_f4(d4 + i, s4[i]);
   } else {
-    for (int i = lane; i < per; i += 32) dst[i] = st[i];
+    __syncwarp();
+    for (int i = lane; i < nd; i += 32) dst[i] = st[i];
   }
   __syncwarp();
 }

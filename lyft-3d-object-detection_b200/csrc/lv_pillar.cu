@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(PIL_WARPS * 32, 6) pillar_decorate_fast_kernel
     if (lane < d.T) a = lv_ld_stream_f4(v + lane);
     if (lane + 32 < d.T) b = lv_ld_stream_f4(v + lane + 32);
     const int num = __ldg(p.num + pil);
+    lv_decorate_zero_tail(num, d, p.out + pil * per, lane);  // independent of the loads above
     const int4 co = __ldg(reinterpret_cast<const int4*>(p.coors) + pil);  // b, z, y, x
     lv_decorate_warp(a, b, num, co.z, co.w, d, st, p.out + pil * per, lane);
   }

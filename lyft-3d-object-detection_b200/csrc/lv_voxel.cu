@@ -61,6 +61,8 @@ struct VoxParams {
   int64_t pt_lo;               // first point of the sub-batch (global point index)
   float lo[3], vs[3];
   int grid[3];                 // gx, gy, gz
+  unsigned div_m[2];           // exact division of a cell id (< 2^28) by gx*gy [0] and by gx [1]:
+  int div_s[2];                //   q = (n * m) >> s   (vx_make_div)
   int64_t G;                   // cells per frame
   int T, V, overflow, zero_tail;
   int low_bits, n_bins;        // bin = vid >> low_bits
@@ -90,6 +92,15 @@ struct ChunkLoc {
   int64_t start;   // global point index of the frame start
   int n;           // points of the frame
 };
+
+// cell id -> (cz, cy, cx) without integer division: m = ceil(2^s / d), s = 28 + ceil(log2 d)
+// is exact for every n < 2^28 (n * (m*d - 2^s) < n * d <= 2^s).
+__device__ __forceinline__ void vx_cell_coords(const VoxParams& p, int c, int& cz, int& cy, int& cx) {
+  cz = (int)(((unsigned long long)(unsigned)c * p.div_m[0]) >> p.div_s[0]);
+  const int rem = c - cz * (p.grid[0] * p.grid[1]);
+  cy = (int)(((unsigned long long)(unsigned)rem * p.div_m[1]) >> p.div_s[1]);
+  cx = rem - cy * p.grid[0];
+}
 
 // One thread resolves the frame of the CTA's chunk by binary search, then broadcasts.
 __device__ __forceinline__ ChunkLoc vx_locate(const VoxParams& p, int* smem4) {
@@ -529,12 +540,12 @@ __global__ void __launch_bounds__(VX_THREADS, 4) vx_bins_kernel(VoxParams p, Dec
   // ---- phase 2: one (sub)warp per voxel writes the output row ----
   const long long row0 = s_row0;
   const int32_t* ccell = p.creator_cell + (fstart - p.pt_lo);
-  const int gx = p.grid[0], gy = p.grid[1];
   if (DECO) {
     const int per = d.T * d.C_out;
     float* st = stage + warp * per;
     const float4* pts4 = reinterpret_cast<const float4*>(p.pts) + fstart;
-    // two pillars per iteration: the point gathers of both are in flight before either is used
+    // two pillars per iteration: the point gathers of both are in flight, and the zero part
+    // of both rows is already streaming out, before either gather is consumed
     for (int v = warp * 2; v < nv; v += VX_WARPS * 2) {
       const long long row = row0 + v0 + v;
       if (row >= p.capacity) break;
@@ -550,8 +561,12 @@ __global__ void __launch_bounds__(VX_THREADS, 4) vx_bins_kernel(VoxParams p, Dec
       if (lane < n1) a1 = __ldg(pts4 + sl[p.T + lane]);
       if (lane + 32 < n1) b1 = __ldg(pts4 + sl[p.T + lane + 32]);
       const int c0 = ccell[v0 + v], c1 = two ? ccell[v0 + v + 1] : 0;
-      const int cx0 = c0 % gx, cy0 = (c0 / gx) % gy, cz0 = c0 / (gx * gy);
-      const int cx1 = c1 % gx, cy1 = (c1 / gx) % gy, cz1 = c1 / (gx * gy);
+      float* dst0 = decorated + row * per;
+      lv_decorate_zero_tail(n0, d, dst0, lane);
+      if (two) lv_decorate_zero_tail(n1, d, dst0 + per, lane);
+      int cx0, cy0, cz0, cx1, cy1, cz1;
+      vx_cell_coords(p, c0, cz0, cy0, cx0);
+      vx_cell_coords(p, c1, cz1, cy1, cx1);
       if (lane == 0) {
         p.num_points[row] = n0;
         *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(f, cz0, cy0, cx0);  // preprocess.py:44-50
@@ -560,8 +575,8 @@ __global__ void __launch_bounds__(VX_THREADS, 4) vx_bins_kernel(VoxParams p, Dec
           *reinterpret_cast<int4*>(p.coords + (row + 1) * 4) = make_int4(f, cz1, cy1, cx1);
         }
       }
-      lv_decorate_warp(a0, b0, n0, cy0, cx0, d, st, decorated + row * per, lane);
-      if (two) lv_decorate_warp(a1, b1, n1, cy1, cx1, d, st, decorated + (row + 1) * per, lane);
+      lv_decorate_warp(a0, b0, n0, cy0, cx0, d, st, dst0, lane);
+      if (two) lv_decorate_warp(a1, b1, n1, cy1, cx1, d, st, dst0 + per, lane);
     }
   } else {
     // LPV lanes per voxel: 32 for pillars, 8 for T <= 8
@@ -576,8 +591,8 @@ __global__ void __launch_bounds__(VX_THREADS, 4) vx_bins_kernel(VoxParams p, Dec
       const int* sl = slot_tab + v * p.T;
       if (sub == 0) {
         p.num_points[row] = n;
-        const int c = ccell[v0 + v];
-        const int cx = c % gx, cy = (c / gx) % gy, cz = c / (gx * gy);
+        int cx, cy, cz;
+        vx_cell_coords(p, ccell[v0 + v], cz, cy, cx);
         if (p.coord_cols == 4) {
           *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(f, cz, cy, cx);
         } else {
@@ -627,6 +642,13 @@ extern "C" int lv_voxel_grid_size(const lv_voxel_config* cfg, int32_t grid_xyz[3
     grid_xyz[j] = (int32_t)rintf(g);
   }
   return LV_OK;
+}
+
+static void vx_make_div(uint32_t d, unsigned* m, int* s) {
+  int lg = 0;
+  while ((1ull << lg) < d) ++lg;
+  *s = 28 + lg;
+  *m = (unsigned)(((1ull << *s) + d - 1) / d);
 }
 
 template <typename K>
@@ -714,6 +736,8 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     p.vs[j] = cfg->voxel_size[j];
     p.grid[j] = grid[j];
   }
+  vx_make_div((uint32_t)grid[0] * (uint32_t)grid[1], &p.div_m[0], &p.div_s[0]);
+  vx_make_div((uint32_t)grid[0], &p.div_m[1], &p.div_s[1]);
   p.G = G; p.T = T; p.V = V; p.overflow = cfg->overflow_mode; p.zero_tail = cfg->zero_tail;
   p.low_bits = L; p.n_bins = n_bins;
   p.voxels = d_voxels; p.coords = d_coords; p.num_points = d_num_points; p.voxel_num = d_voxel_num;
