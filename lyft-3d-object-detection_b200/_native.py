@@ -85,7 +85,7 @@ SIGNATURES = {
 }
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()  # get_handle -> Handle() -> load() re-enters
 _handles = {}  # (pid, device) -> handle
 
 

@@ -157,6 +157,14 @@ int lv_set_option(lv_handle* h, const char* name, int64_t value) {
     h->bev_frames_in_flight = value;
     return LV_OK;
   }
+  if (strcmp(name, "bev_tma") == 0) {
+    h->bev_tma = value;
+    return LV_OK;
+  }
+  if (strcmp(name, "disable_tma") == 0) {
+    h->disable_tma = value;
+    return LV_OK;
+  }
   if (strcmp(name, "vox_dense_map_limit_bytes") == 0) {
     h->vox_dense_map_limit_bytes = value;
     return LV_OK;

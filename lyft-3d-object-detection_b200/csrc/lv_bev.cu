@@ -20,6 +20,8 @@
 //   bev_finalize_*       one pass over the counts of the frames in flight: emits every
 //                        requested output and clears the counts.
 //                        Algorithmic bytes: 4 (raw) [+4 norm] [+1 u8] [+ (S2+3)*4/S2 chw + 1 map] per cell.
+#include <algorithm>
+
 #include "lv_common.cuh"
 
 struct BevParams {
@@ -35,6 +37,8 @@ struct BevParams {
   int S0, S1, S2;
   unsigned cells;
   unsigned* counts;
+  unsigned* dirty;             // 1 bit per 4 consecutive counts ("quad"): set by the first hit of a cell
+  int use_tma;                 // point rows 16-byte aligned: full tiles are staged by TMA bulk copies
 };
 
 __device__ __forceinline__ int bev_find_segment(const int64_t* __restrict__ offs, int lo, int hi, int64_t i) {
@@ -45,56 +49,149 @@ __device__ __forceinline__ int bev_find_segment(const int64_t* __restrict__ offs
   }
   return lo;
 }
+// the same for a warp-uniform i: a 32-ary search, one coalesced load per round (all lanes must call)
+__device__ __forceinline__ int bev_find_segment_warp(const int64_t* __restrict__ offs, int lo, int hi, int64_t i, int lane) {
+  while (hi - lo > 1) {
+    const int step = (hi - lo + 31) >> 5;
+    const int cand = lo + lane * step;
+    const bool ok = cand < hi && __ldg(offs + cand) <= i;   // monotone in lane; lane 0 always holds
+    const int j = 31 - __clz(__ballot_sync(0xffffffffu, ok));
+    lo += j * step;
+    hi = lo + step < hi ? lo + step : hi;
+  }
+  return lo;
+}
 
-template <bool STRIDE4>
-__global__ void __launch_bounds__(256) bev_hist_kernel(BevParams p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  // warp-uniform trip count so that every lane reaches __match_any_sync
-  for (int64_t base = p.pt_begin + (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
-       base < p.pt_end; base += step) {
-    const int64_t i = base + lane;
-    unsigned key = 0xffffffffu;
-    if (i < p.pt_end) {
-      float x, y, z;
-      if (STRIDE4) {
-        float4 v = lv_ld_stream_f4(reinterpret_cast<const float4*>(p.pts) + i);
-        x = v.x; y = v.y; z = v.z;
-      } else {
-        const float* q = p.pts + i * p.stride;
-        x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
+#define BEV_THREADS 256
+#define BEV_WARPS (BEV_THREADS / 32)
+#define BEV_ITEMS 4
+#define BEV_WTILE (32 * BEV_ITEMS)          // 128 points per warp
+#define BEV_TILE (BEV_THREADS * BEV_ITEMS)  // 1024 points per tile
+#define BEV_STAGES 4                         // tiles in flight per CTA (TMA pipeline depth)
+
+// Persistent CTAs walk the tiles of the sub-batch (tile t = absolute points [t*1024, (t+1)*1024));
+// a warp owns a contiguous span of 128 points of the tile.  STRIDE 4 / 5: tiles that lie
+// entirely inside the sub-batch are staged in shared memory by one TMA bulk copy each
+// (cp.async.bulk + mbarrier, four stages: the copies of the CTA's next three tiles are in
+// flight while the current one is processed) and read back with conflict-free LDS (a row stride of 5 words
+// is coprime with the 32 banks).  STRIDE 0: any row stride, direct global loads.
+template <int STRIDE>
+__global__ void __launch_bounds__(BEV_THREADS) bev_hist_kernel(BevParams p) {
+  extern __shared__ __align__(128) float tiles[];  // [BEV_STAGES][BEV_TILE * STRIDE]
+  __shared__ __align__(8) uint64_t bar[BEV_STAGES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t_lo = p.pt_begin / BEV_TILE, t_hi = (p.pt_end + BEV_TILE - 1) / BEV_TILE;
+  const bool tma = STRIDE != 0 && p.use_tma;
+  constexpr unsigned TILE_FLOATS = BEV_TILE * (STRIDE ? STRIDE : 1);
+  if (tma) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < BEV_STAGES; ++s) lv_mbar_init(&bar[s], 1);
+      lv_mbar_init_fence();
+    }
+    __syncthreads();
+  }
+  unsigned phase = 0;  // bit s = parity the next fill of stage s completes with
+  int64_t t = t_lo + blockIdx.x;
+  const int64_t t_step = gridDim.x;
+  auto staged = [&](int64_t tt) { return tma && tt < t_hi && tt * BEV_TILE >= p.pt_begin && (tt + 1) * BEV_TILE <= p.pt_end; };
+  auto issue = [&](int64_t tt, int s) {
+    lv_mbar_expect_tx(&bar[s], TILE_FLOATS * 4);
+    lv_tma_load_1d(tiles + (size_t)s * TILE_FLOATS, p.pts + tt * (int64_t)TILE_FLOATS, TILE_FLOATS * 4, &bar[s]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < BEV_STAGES - 1; ++s)
+      if (staged(t + s * t_step)) issue(t + s * t_step, s);
+  }
+  // results of the ATOMs of the previous tile (was the cell empty?): looked at one tile later,
+  // when they have long arrived
+  unsigned pend_key[BEV_ITEMS], pend_old[BEV_ITEMS];
+#pragma unroll
+  for (int r = 0; r < BEV_ITEMS; ++r) { pend_key[r] = 0xffffffffu; pend_old[r] = 1; }
+  for (unsigned k = 0; t < t_hi; t += t_step, ++k) {
+    const int s = k % BEV_STAGES;
+    // stage (k-1) % STAGES was released by the barrier that ended the previous iteration
+    if (threadIdx.x == 0 && staged(t + (BEV_STAGES - 1) * t_step))
+      issue(t + (BEV_STAGES - 1) * t_step, (k + BEV_STAGES - 1) % BEV_STAGES);
+    // segments of the warp's span (uniform across the warp), looked up while the copy is in flight
+    const int64_t span0 = t * BEV_TILE + warp * BEV_WTILE;
+    const int64_t v0 = span0 < p.pt_begin ? p.pt_begin : span0;
+    const int64_t v1 = span0 + BEV_WTILE < p.pt_end ? span0 + BEV_WTILE : p.pt_end;  // valid points [v0, v1)
+    int sa = p.seg_lo, sb = p.seg_lo;
+    if (v0 < v1 && p.seg_hi - p.seg_lo > 1) {
+      sa = bev_find_segment_warp(p.seg_offsets, p.seg_lo, p.seg_hi, v0, lane);
+      sb = sa;
+      if (__ldg(p.seg_offsets + sa + 1) < v1) sb = bev_find_segment_warp(p.seg_offsets, sa, p.seg_hi, v1 - 1, lane);
+    }
+    const bool in_smem = staged(t);
+    if (in_smem) {
+      lv_mbar_wait(&bar[s], (phase >> s) & 1);
+      phase ^= 1u << s;
+    }
+    const float* buf = tiles + (size_t)s * TILE_FLOATS;
+#pragma unroll
+    for (int r = 0; r < BEV_ITEMS; ++r) {
+      const int li = warp * BEV_WTILE + r * 32 + lane;
+      const int64_t i = t * BEV_TILE + li;
+      unsigned key = 0xffffffffu;
+      if (i >= v0 && i < v1) {
+        float x, y, z;
+        if (STRIDE == 4) {
+          float4 v;
+          if (in_smem) v = reinterpret_cast<const float4*>(buf)[li];
+          else v = lv_ld_stream_f4(reinterpret_cast<const float4*>(p.pts) + i);
+          x = v.x; y = v.y; z = v.z;
+        } else if (STRIDE != 0 && in_smem) {
+          x = buf[li * STRIDE]; y = buf[li * STRIDE + 1]; z = buf[li * STRIDE + 2];
+        } else {
+          const float* q = p.pts + i * p.stride;
+          x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
+        }
+        int seg = sa;
+        if (sb != sa) seg = bev_find_segment(p.seg_offsets, sa, sb + 1, i);
+        if (p.seg_tm) {
+          // PointCloud.transform (data_classes.py:195): float64 product, float32 store.
+          const double* M = p.seg_tm + (size_t)seg * 16;
+          const double X = x, Y = y, Z = z;
+          double ax = fma(__ldg(M + 2), Z, fma(__ldg(M + 1), Y, __ldg(M + 0) * X)) + __ldg(M + 3);
+          double ay = fma(__ldg(M + 6), Z, fma(__ldg(M + 5), Y, __ldg(M + 4) * X)) + __ldg(M + 7);
+          double az = fma(__ldg(M + 10), Z, fma(__ldg(M + 9), Y, __ldg(M + 8) * X)) + __ldg(M + 11);
+          x = (float)ax; y = (float)ay; z = (float)az;
+        }
+        // car_to_voxel_coords (generating_train_bev.py:47-82): un-fused fp64 multiply then add.
+        const double u0 = __dadd_rn(__dmul_rn(p.m0, (double)x), p.t0);
+        const double u1 = __dadd_rn(__dmul_rn(p.m1, (double)y), p.t1);
+        const double u2 = __dadd_rn(__dmul_rn(p.m2, (double)z), p.t2);
+        // trunc(u) in [0, S)  <=>  -1 < u < S ; NaN fails (np.intp(nan) is out of bounds).
+        const bool in = (u0 > -1.0) && (u0 < (double)p.S0) && (u1 > -1.0) && (u1 < (double)p.S1) &&
+                        (u2 > -1.0) && (u2 < (double)p.S2);
+        if (in) {
+          const int c0 = (int)u0, c1 = (int)u1, c2 = (int)u2;  // C truncation == np.intp
+          const int frame = p.seg_frame ? __ldg(p.seg_frame + seg) : seg;
+          key = (unsigned)(frame - p.frame_base) * p.cells + (unsigned)((c1 * p.S1 + c0) * p.S2 + c2);
+        }
       }
-      int seg = p.seg_lo;
-      if (p.seg_hi - p.seg_lo > 1) seg = bev_find_segment(p.seg_offsets, p.seg_lo, p.seg_hi, i);
-      if (p.seg_tm) {
-        // PointCloud.transform (data_classes.py:195): float64 product, float32 store.
-        const double* M = p.seg_tm + (size_t)seg * 16;
-        const double X = x, Y = y, Z = z;
-        double ax = fma(__ldg(M + 2), Z, fma(__ldg(M + 1), Y, __ldg(M + 0) * X)) + __ldg(M + 3);
-        double ay = fma(__ldg(M + 6), Z, fma(__ldg(M + 5), Y, __ldg(M + 4) * X)) + __ldg(M + 7);
-        double az = fma(__ldg(M + 10), Z, fma(__ldg(M + 9), Y, __ldg(M + 8) * X)) + __ldg(M + 11);
-        x = (float)ax; y = (float)ay; z = (float)az;
-      }
-      // car_to_voxel_coords (generating_train_bev.py:47-82): un-fused fp64 multiply then add.
-      const double u0 = __dadd_rn(__dmul_rn(p.m0, (double)x), p.t0);
-      const double u1 = __dadd_rn(__dmul_rn(p.m1, (double)y), p.t1);
-      const double u2 = __dadd_rn(__dmul_rn(p.m2, (double)z), p.t2);
-      // trunc(u) in [0, S)  <=>  -1 < u < S ; NaN fails (np.intp(nan) is out of bounds).
-      const bool in = (u0 > -1.0) && (u0 < (double)p.S0) && (u1 > -1.0) && (u1 < (double)p.S1) &&
-                      (u2 > -1.0) && (u2 < (double)p.S2);
-      if (in) {
-        const int c0 = (int)u0, c1 = (int)u1, c2 = (int)u2;  // C truncation == np.intp
-        const int frame = p.seg_frame ? __ldg(p.seg_frame + seg) : seg;
-        key = (unsigned)(frame - p.frame_base) * p.cells + (unsigned)((c1 * p.S1 + c0) * p.S2 + c2);
+      // warp-aggregated atomics: one ATOM per distinct cell per warp.  The first hit of a cell
+      // (old == 0) marks the cell's quad in the dirty bitmap.
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (pend_old[r] == 0) atomicOr(p.dirty + (pend_key[r] >> 7), 1u << ((pend_key[r] >> 2) & 31));
+      pend_key[r] = 0xffffffffu;
+      pend_old[r] = 1;
+      if (key != 0xffffffffu && lane == (__ffs(peers) - 1)) {
+        pend_old[r] = atomicAdd(p.counts + key, (unsigned)__popc(peers));
+        pend_key[r] = key;
       }
     }
-    // warp-aggregated atomics: one RED per distinct cell per warp
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (key != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(p.counts + key, (unsigned)__popc(peers));
+    if (tma) __syncthreads();  // every thread is done with stage s before it is refilled
   }
+#pragma unroll
+  for (int r = 0; r < BEV_ITEMS; ++r)
+    if (pend_old[r] == 0) atomicOr(p.dirty + (pend_key[r] >> 7), 1u << ((pend_key[r] >> 2) & 31));
 }
 
 struct BevOut {
+  unsigned* dirty;     // see BevParams
   float* raw;
   float* norm;
   uint8_t* u8;
@@ -113,49 +210,90 @@ __device__ __forceinline__ void bev_cell(unsigned c, float max_intensity, float&
   q = (uint8_t)rintf(__fmul_rn(nrm, 255.0f));                      // np.round(bev*255).astype(uint8), :213
 }
 
-// flat path: 4 consecutive cells per thread-item (cells % 4 == 0).  grid = (x, frames in
-// flight); 4 independent 128-bit loads are issued before any store (memory-level parallelism).
-#define BEV_FIN_UNROLL 4
+// The grid is sparse (2% of the cells of a Lyft sweep are hit): the finalize kernels read the
+// dirty bitmap (1 bit per quad of counts) instead of the counts, load - and clear - only the
+// dirty quads, and stream the dense outputs.  A quad's bit is cleared by the one thread that
+// owns the quad, so counts and bitmap are all-zero again when the kernel ends.
+// flat path (cells % 4 == 0): the counts of the frames in flight are one flat array of quads.
+// A warp task = 1024 consecutive quads = 32 words of the bitmap (lane l holds word l, one
+// coalesced load).  Pass A streams zeros over the whole task - it depends on nothing, so the
+// store stream never waits; pass B revisits only the dirty quads (2-7% on a Lyft sweep): loads
+// and clears their counts, four independent loads at a time, and overwrites the outputs.
 __global__ void __launch_bounds__(256) bev_finalize_flat4_kernel(unsigned* counts, BevOut o) {
-  const unsigned quads = o.cells / 4;
-  const unsigned f = blockIdx.y;
-  uint4* cp = reinterpret_cast<uint4*>(counts) + (size_t)f * quads;
-  const size_t out0 = (size_t)(o.frame_base + f) * quads;
+  const int lane = threadIdx.x & 31;
+  const int64_t total_quads = (int64_t)(o.cells / 4) * o.n_frames;
+  const int64_t n_tasks = (total_quads + 1023) >> 10;
+  const int64_t out0 = (int64_t)o.frame_base * (o.cells / 4);
+  uint4* cp = reinterpret_cast<uint4*>(counts);
   float4* raw = o.raw ? reinterpret_cast<float4*>(o.raw) + out0 : nullptr;
   float4* nrm = o.norm ? reinterpret_cast<float4*>(o.norm) + out0 : nullptr;
   uchar4* u8 = o.u8 ? reinterpret_cast<uchar4*>(o.u8) + out0 : nullptr;
-  for (unsigned q0 = blockIdx.x * (256 * BEV_FIN_UNROLL) + threadIdx.x; q0 < quads;
-       q0 += gridDim.x * (256 * BEV_FIN_UNROLL)) {
-    uint4 c[BEV_FIN_UNROLL];
-#pragma unroll
-    for (int k = 0; k < BEV_FIN_UNROLL; ++k) {
-      const unsigned q = q0 + k * 256;
-      c[k] = q < quads ? cp[q] : make_uint4(0, 0, 0, 0);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uchar4 zb = make_uchar4(0, 0, 0, 0);
+  for (int64_t task = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); task < n_tasks; task += (int64_t)gridDim.x * 8) {
+    const int64_t q0 = task << 10;
+    const int64_t w = (q0 >> 5) + lane;
+    unsigned word = 0;
+    if ((w << 5) < total_quads) {
+      word = o.dirty[w];
+      if (word) o.dirty[w] = 0;   // the warp owns these 32 words
     }
+    // pass A
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const int64_t q = q0 + k * 32 + lane;
+      if (q < total_quads) {
+        if (raw) lv_st_stream_f4(raw + q, z4);
+        if (nrm) lv_st_stream_f4(nrm + q, z4);
+        if (u8) u8[q] = zb;
+      }
+    }
+    if (!__any_sync(0xffffffffu, word != 0)) continue;
+    // pass B: lane l revisits the dirty quads of its column (quads q0 + 32 k + l, bit l of
+    // word k): same thread as in pass A, coalesced with its neighbours, four loads in flight
+    unsigned col = 0;
 #pragma unroll
-    for (int k = 0; k < BEV_FIN_UNROLL; ++k) {
-      const unsigned q = q0 + k * 256;
-      if (q >= quads) break;
-      if (c[k].x | c[k].y | c[k].z | c[k].w) cp[q] = make_uint4(0, 0, 0, 0);   // only dirty quads are rewritten
-      float4 r, n;
-      uchar4 b;
-      bev_cell(c[k].x, o.max_intensity, r.x, n.x, b.x);
-      bev_cell(c[k].y, o.max_intensity, r.y, n.y, b.y);
-      bev_cell(c[k].z, o.max_intensity, r.z, n.z, b.z);
-      bev_cell(c[k].w, o.max_intensity, r.w, n.w, b.w);
-      if (raw) lv_st_stream_f4(raw + q, r);
-      if (nrm) lv_st_stream_f4(nrm + q, n);
-      if (u8) u8[q] = b;
+    for (int k = 0; k < 32; ++k) col |= ((__shfl_sync(0xffffffffu, word, k) >> lane) & 1u) << k;
+    while (__any_sync(0xffffffffu, col != 0)) {
+      int64_t q[4];
+      uint4 c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        q[j] = -1;
+        if (col) {
+          q[j] = q0 + (__ffs(col) - 1) * 32 + lane;
+          col &= col - 1;
+          c[j] = cp[q[j]];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (q[j] < 0) continue;
+        cp[q[j]] = make_uint4(0, 0, 0, 0);
+        float4 r, n;
+        uchar4 b;
+        bev_cell(c[j].x, o.max_intensity, r.x, n.x, b.x);
+        bev_cell(c[j].y, o.max_intensity, r.y, n.y, b.y);
+        bev_cell(c[j].z, o.max_intensity, r.z, n.z, b.z);
+        bev_cell(c[j].w, o.max_intensity, r.w, n.w, b.w);
+        if (raw) raw[q[j]] = r;      // same thread, same address as its pass-A store: ordered
+        if (nrm) nrm[q[j]] = n;
+        if (u8) u8[q[j]] = b;
+      }
     }
   }
 }
 
+// any cell count (cells % 4 != 0): one thread per cell; the bitmap is cleared by a memset after
 __global__ void __launch_bounds__(256) bev_finalize_scalar_kernel(unsigned* counts, BevOut o) {
   const int64_t total = (int64_t)o.cells * o.n_frames;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
        q += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned c = counts[q];
-    counts[q] = 0;
+    unsigned c = 0;
+    if (o.dirty[q >> 7] & (1u << ((q >> 2) & 31))) {
+      c = counts[q];
+      counts[q] = 0;
+    }
     const int64_t out_q = o.frame_base * (int64_t)o.cells + q;
     float r, n;
     uint8_t b;
@@ -175,14 +313,23 @@ __global__ void __launch_bounds__(256) bev_finalize_hwc3_kernel(unsigned* counts
        g += (int64_t)gridDim.x * blockDim.x) {
     const int64_t f = g / groups_per_frame;
     const int64_t gi = g - f * groups_per_frame;        // (y, x/4) flattened: y*(S1/4) + x4
-    uint4* cp = reinterpret_cast<uint4*>(counts) + g * 3;  // 12 consecutive counts
+    uint4* cp = reinterpret_cast<uint4*>(counts) + g * 3;  // 12 consecutive counts = 3 quads
     unsigned c[12];
-    *reinterpret_cast<uint4*>(c + 0) = cp[0];
-    *reinterpret_cast<uint4*>(c + 4) = cp[1];
-    *reinterpret_cast<uint4*>(c + 8) = cp[2];
-    cp[0] = make_uint4(0, 0, 0, 0);
-    cp[1] = make_uint4(0, 0, 0, 0);
-    cp[2] = make_uint4(0, 0, 0, 0);
+    bool dirty[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {   // the three bitmap loads, then the three count loads, are independent
+      const unsigned gq = (unsigned)(g * 3 + k);
+      dirty[k] = (o.dirty[gq >> 5] >> (gq & 31)) & 1u;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) *reinterpret_cast<uint4*>(c + 4 * k) = dirty[k] ? cp[k] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (!dirty[k]) continue;
+      const unsigned gq = (unsigned)(g * 3 + k);
+      cp[k] = make_uint4(0, 0, 0, 0);
+      atomicAnd(o.dirty + (gq >> 5), ~(1u << (gq & 31)));   // this thread owns the quad's bit
+    }
     float r[12], n[12];
     uint8_t b[12];
 #pragma unroll
@@ -298,6 +445,8 @@ extern "C" int lv_bev_rasterize(lv_handle* h, const float* d_points, int32_t poi
   fif = lv_div_up(n_frames, lv_div_up(n_frames, fif));
   while (fif > 1 && fif * cells64 >= 0xffffffffll) --fif;
   LV_CHECK(h->bev_counts.ensure((size_t)fif * cells * sizeof(unsigned), stream, 0));
+  const size_t dirty_bytes = (size_t)(lv_div_up(fif * cells64, 128) + 32) * sizeof(unsigned);
+  LV_CHECK(h->bev_dirty.ensure(dirty_bytes, stream, 0));
 
   const void *d_off = nullptr, *d_frame = nullptr, *d_tm = nullptr;
   if (n_segments > 0) {
@@ -323,8 +472,17 @@ extern "C" int lv_bev_rasterize(lv_handle* h, const float* d_points, int32_t poi
   p.S0 = shape[0]; p.S1 = shape[1]; p.S2 = shape[2];
   p.cells = cells;
   p.counts = h->bev_counts.as<unsigned>();
+  p.dirty = h->bev_dirty.as<unsigned>();
+  // TMA bulk copies need 16-byte aligned tiles: tile t starts at byte t * 1024 * stride * 4
+  p.use_tma = (point_stride == 4 || point_stride == 5) && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0 &&
+              h->bev_tma && !h->disable_tma;
+  if (point_stride == 4)
+    LV_CHECK_CUDA(cudaFuncSetAttribute(bev_hist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BEV_STAGES * BEV_TILE * 16));
+  if (point_stride == 5)
+    LV_CHECK_CUDA(cudaFuncSetAttribute(bev_hist_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, BEV_STAGES * BEV_TILE * 20));
 
   BevOut o;
+  o.dirty = p.dirty;
   o.raw = d_raw; o.norm = d_norm; o.u8 = d_u8; o.map = d_map_u8; o.chw = d_chw;
   o.max_intensity = max_intensity;
   o.cells = cells; o.S0 = shape[0]; o.S1 = shape[1]; o.S2 = shape[2];
@@ -343,11 +501,18 @@ extern "C" int lv_bev_rasterize(lv_handle* h, const float* d_points, int32_t poi
       p.pt_end = h_seg_offsets[s1];
       const int64_t npts = p.pt_end - p.pt_begin;
       if (npts > 0) {
-        const int grid = bev_grid(h, npts, 8);
-        if (point_stride == 4 && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0)
-          bev_hist_kernel<true><<<grid, 256, 0, stream>>>(p);
-        else
-          bev_hist_kernel<false><<<grid, 256, 0, stream>>>(p);
+        const int64_t n_tiles = lv_div_up(p.pt_end, BEV_TILE) - p.pt_begin / BEV_TILE;
+        if (point_stride == 4 && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0) {
+          const size_t smem = p.use_tma ? BEV_STAGES * BEV_TILE * 16 : 0;   // 64 KB: 3 CTAs per SM
+          const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)h->num_sms * (p.use_tma ? 3 : 8));
+          bev_hist_kernel<4><<<grid, BEV_THREADS, smem, stream>>>(p);
+        } else if (point_stride == 5 && p.use_tma) {
+          const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)h->num_sms * 2);   // 80 KB: 2 CTAs per SM
+          bev_hist_kernel<5><<<grid, BEV_THREADS, BEV_STAGES * BEV_TILE * 20, stream>>>(p);
+        } else {
+          const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)h->num_sms * 8);
+          bev_hist_kernel<0><<<grid, BEV_THREADS, 0, stream>>>(p);
+        }
         LV_LAUNCH_CHECK(h);
       }
     }
@@ -357,13 +522,12 @@ extern "C" int lv_bev_rasterize(lv_handle* h, const float* d_points, int32_t poi
       const int64_t items = (int64_t)o.n_frames * shape[0] * (shape[1] / 4);
       bev_finalize_hwc3_kernel<<<bev_grid(h, items, 8), 256, 0, stream>>>(p.counts, o);
     } else if (cells % 4 == 0) {
-      int gx = (int)lv_div_up(cells / 4, 256 * BEV_FIN_UNROLL);
-      const int want = (int)lv_div_up((int64_t)h->num_sms * 8, o.n_frames);
-      if (gx > want) gx = want < 1 ? 1 : want;
-      bev_finalize_flat4_kernel<<<dim3((unsigned)gx, (unsigned)o.n_frames), 256, 0, stream>>>(p.counts, o);
+      const int64_t tasks = lv_div_up((int64_t)(cells / 4) * o.n_frames, 1024);
+      bev_finalize_flat4_kernel<<<bev_grid(h, tasks * 32, 8), 256, 0, stream>>>(p.counts, o);
     } else {
       const int64_t items = (int64_t)o.n_frames * cells;
       bev_finalize_scalar_kernel<<<bev_grid(h, items, 8), 256, 0, stream>>>(p.counts, o);
+      LV_CHECK_CUDA(cudaMemsetAsync(p.dirty, 0, dirty_bytes, stream));
     }
     LV_LAUNCH_CHECK(h);
   }

@@ -69,9 +69,15 @@ struct lv_handle {
   // options
   int64_t bev_frames_in_flight = 0;   // 0 = auto
   int64_t vox_dense_map_limit_bytes = 0;
+  int64_t disable_tma = 0;            // 1: no kernel stages point tiles by TMA (A/B measurements)
+  int64_t bev_tma = 0;                // 1: bev_hist_kernel stages its tiles by TMA.  Off by default: measured
+                                      // slower than plain loads (tools/ab_tma.py: 0.176 vs 0.154 ms stride 4,
+                                      // 0.203 vs 0.158 ms stride 5, 128 frames) - the kernel is bound by the
+                                      // L2 atomics, not by the loads
 
   // BEV
   lv_buffer bev_counts;               // u32 [frames_in_flight][cells], kept all-zero between calls
+  lv_buffer bev_dirty;                // 1 bit per 4 counts, kept all-zero between calls
   lv_mirror bev_seg_offsets, bev_seg_frame, bev_seg_tm;
   lv_buffer bev_stage_points, bev_stage_out[5], bev_stage_map;  // *_host staging
 
@@ -88,7 +94,7 @@ struct lv_handle {
 
 // every device buffer a handle owns (for lv_destroy / lv_workspace_bytes)
 inline std::vector<lv_buffer*> lv_all_buffers(lv_handle* h) {
-  return {&h->bev_counts, &h->bev_seg_offsets.dev, &h->bev_seg_frame.dev, &h->bev_seg_tm.dev, &h->bev_stage_points,
+  return {&h->bev_counts, &h->bev_dirty, &h->bev_seg_offsets.dev, &h->bev_seg_frame.dev, &h->bev_seg_tm.dev, &h->bev_stage_points,
           &h->bev_stage_out[0], &h->bev_stage_out[1], &h->bev_stage_out[2], &h->bev_stage_out[3], &h->bev_stage_out[4],
           &h->bev_stage_map, &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1], &h->vox_vals[0],
           &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state, &h->vox_row_base,
@@ -118,6 +124,39 @@ __device__ __forceinline__ void lv_st_stream_f4(float4* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
                "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
+}
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier: stages tiles of point rows
+// in shared memory.  Source and destination 16-byte aligned, size a multiple of 16 bytes.
+__device__ __forceinline__ uint32_t lv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lv_mbar_init(uint64_t* bar, unsigned arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lv_smem_u32(bar)), "r"(arrivals) : "memory");
+}
+// makes the initialised barriers visible to the async proxy; follow with __syncthreads()
+__device__ __forceinline__ void lv_mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void lv_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lv_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lv_tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   lv_smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(lv_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void lv_mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LV_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LV_DONE_%=;\n"
+      "bra LV_WAIT_%=;\n"
+      "LV_DONE_%=:\n"
+      "}\n" ::"r"(lv_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 __device__ __forceinline__ unsigned lv_lanemask_lt() {
   unsigned m;

@@ -65,6 +65,7 @@ struct VoxParams {
   int div_s[2];                //   q = (n * m) >> s   (vx_make_div)
   int64_t G;                   // cells per frame
   int T, V, overflow, zero_tail;
+  unsigned tma_bytes;          // bytes of one full chunk of rows when K1 stages them by TMA, else 0
   int low_bits, n_bins;        // bin = vid >> low_bits
   // workspace (indexed relative to the sub-batch)
   int32_t* map;                // [f1-f0][G]
@@ -126,27 +127,49 @@ __device__ __forceinline__ ChunkLoc vx_locate(const VoxParams& p, int* smem4) {
 }
 
 // ---------------------------------------------------------------- K1: cells + first index
+// A full chunk (2048 rows) whose first row is 16-byte aligned is staged in shared memory by
+// one TMA bulk copy (cp.async.bulk + mbarrier); partial or unaligned chunks use plain loads.
 template <bool C4>
 __global__ void __launch_bounds__(VX_THREADS) vx_cells_kernel(VoxParams p) {
+  extern __shared__ __align__(128) float tile[];  // [VX_CHUNK][C] when p.tma_bytes != 0
+  __shared__ __align__(8) uint64_t bar;
   __shared__ int sm[4];
   const ChunkLoc L = vx_locate(p, sm);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = p.pts + (L.start + (int64_t)L.c * VX_CHUNK) * p.C;
+  const bool staged = p.tma_bytes != 0 && (L.c + 1) * VX_CHUNK <= L.n && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
   if (threadIdx.x == 0) {
+    if (staged) {
+      lv_mbar_init(&bar, 1);
+      lv_mbar_init_fence();
+      lv_mbar_expect_tx(&bar, p.tma_bytes);
+      lv_tma_load_1d(tile, src, p.tma_bytes, &bar);
+    }
     p.chunk_state[blockIdx.x] = 0ull;                // look-back descriptor of this chunk: invalid
     if (L.c == 0) p.frame_cut[L.fl] = 0x7fffffff;
   }
   int32_t* map = p.map + (int64_t)L.fl * p.G;
+  if (staged) {
+    __syncthreads();  // the barrier is initialised
+    lv_mbar_wait(&bar, 0);
+  }
   const int base = L.c * VX_CHUNK + warp * (32 * VX_ITEMS);
 #pragma unroll 2
   for (int r = 0; r < VX_ITEMS; ++r) {
-    const int li = base + r * 32 + lane;  // local point index inside the frame
+    const int ti = warp * (32 * VX_ITEMS) + r * 32 + lane;  // row inside the chunk
+    const int li = base + r * 32 + lane;                    // local point index inside the frame
     int cell = -1;
     if (li < L.n) {
       const int64_t gi = L.start + li;
       float x, y, z;
       if (C4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p.pts) + gi);
+        float4 v;
+        if (staged) v = reinterpret_cast<const float4*>(tile)[ti];
+        else v = __ldg(reinterpret_cast<const float4*>(p.pts) + gi);
         x = v.x; y = v.y; z = v.z;
+      } else if (staged) {
+        const float* q = tile + ti * p.C;
+        x = q[0]; y = q[1]; z = q[2];
       } else {
         const float* q = p.pts + gi * p.C;
         x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
@@ -759,6 +782,11 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   memset(&dcfg, 0, sizeof(dcfg));
   if (deco) dcfg = *deco;
 
+  // K1 stages full chunks by TMA when a chunk of rows is a multiple of 16 bytes and fits 64 KB
+  p.tma_bytes = 0;
+  if (!h->disable_tma && C <= 8 && ((size_t)VX_CHUNK * C * 4) % 16 == 0) p.tma_bytes = (unsigned)(VX_CHUNK * C * 4);
+  if (c4) LV_CHECK(vx_set_smem(vx_cells_kernel<true>, p.tma_bytes));
+  else LV_CHECK(vx_set_smem(vx_cells_kernel<false>, p.tma_bytes));
   LV_CHECK(vx_set_smem(vx_keys_kernel, smem_keys));
   LV_CHECK(vx_set_smem(vx_scatter_kernel, smem_scatter));
   if (deco) LV_CHECK(vx_set_smem(vx_bins_kernel<true, true>, smem_bins));
@@ -794,8 +822,8 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     p.frame_kept = p.frame_cut + nf;
 
     if (nchunks > 0) {
-      if (c4) vx_cells_kernel<true><<<nchunks, VX_THREADS, 0, stream>>>(p);
-      else vx_cells_kernel<false><<<nchunks, VX_THREADS, 0, stream>>>(p);
+      if (c4) vx_cells_kernel<true><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
+      else vx_cells_kernel<false><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
       LV_LAUNCH_CHECK(h);
       vx_assign_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p);
       LV_LAUNCH_CHECK(h);

@@ -41,6 +41,10 @@ class FrameBatchEngine:
         import os as _os
         if _os.environ.get("LV_VOX_MAP_MB"):
             self.h.set_option("vox_dense_map_limit_bytes", int(_os.environ["LV_VOX_MAP_MB"]) << 20)
+        if _os.environ.get("LV_BEV_TMA"):
+            self.h.set_option("bev_tma", int(_os.environ["LV_BEV_TMA"]))
+        if _os.environ.get("LV_DISABLE_TMA"):
+            self.h.set_option("disable_tma", int(_os.environ["LV_DISABLE_TMA"]))
         if _os.environ.get("LV_BEV_FIF"):
             self.h.set_option("bev_frames_in_flight", int(_os.environ["LV_BEV_FIF"]))
         self.F = int(frames_per_step)

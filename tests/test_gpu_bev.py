@@ -162,3 +162,43 @@ def test_many_small_frames_exceeding_frames_in_flight(bev, bo):
     total = sum(int(bo.create_voxel_pointcloud(np.ascontiguousarray(fr.T), synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE,
                                                synth.BEV_Z_OFFSET).sum()) for fr in frames)
     assert int(res["raw"].sum(dtype=np.float64)) == total
+
+
+@pytest.mark.parametrize("stride", [4, 5])
+def test_tma_staged_tiles_ragged_frames_and_unaligned_views(bev, bo, stride):
+    """Tiles of 2048 rows are staged by TMA bulk copies when the rows are 16-byte aligned;
+    ragged frames make tiles straddle frame boundaries, a row-offset view breaks the
+    alignment (stride 5) and must take the plain-load path; the TMA path (option `bev_tma`,
+    off by default because it measured slower) must not change a single count."""
+    import torch
+    from lyft3d_b200 import _native as nat
+    raw5 = synth.load_fixture_raw()
+    sizes = [2048, 1, 4095, 0, 6151, 777, 20000, 33]
+    rng = np.random.default_rng(77)
+    frames = []
+    for f, n in enumerate(sizes):
+        sel = rng.integers(0, raw5.shape[0], size=n)
+        fr = raw5[sel].copy()
+        fr[:, 0] += 0.37 * f
+        frames.append(np.ascontiguousarray(fr[:, :stride]))
+    rows = np.concatenate(frames, axis=0)
+    offs = np.zeros(len(sizes) + 1, np.int64)
+    offs[1:] = np.cumsum(sizes)
+    refs = [bo.create_voxel_pointcloud(np.ascontiguousarray(fr[:, :4].T), synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE,
+                                       synth.BEV_Z_OFFSET) for fr in frames]
+    h = nat.get_handle(0)
+    pad = torch.zeros((rows.shape[0] + 3, stride), dtype=torch.float32, device="cuda")
+    for shift in (0, 1, 3):           # shift != 0 with stride 5 -> rows not 16-byte aligned
+        view = pad[shift:shift + rows.shape[0]]
+        view.copy_(torch.from_numpy(rows))
+        for on in (1, 0):
+            h.set_option("bev_tma", on)
+            try:
+                res = bev.rasterize_frames(view, offs, synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE, synth.BEV_Z_OFFSET,
+                                           want=("raw", "u8"))
+            finally:
+                h.set_option("bev_tma", 0)
+            got = res["raw"].cpu().numpy()
+            for f in range(len(sizes)):
+                assert np.array_equal(got[f], refs[f]), (stride, shift, on, f)
+            assert np.array_equal(res["u8"][2].cpu().numpy(), bo.quantize_u8(bo.normalize_voxel_intensities(refs[2])))
