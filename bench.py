@@ -277,6 +277,26 @@ def main():
             stage_ms[st] += e[i].elapsed_time(e[i + 1])
     mean_rows = sum(rows_seen) / max(len(rows_seen), 1)
 
+    # ---- reported separately (not part of `value`): the pillar path with the
+    # PFNLayer fused behind the decoration - points -> (rows, 64) features -> canvas
+    from lyft3d_b200 import pointpillars as pp
+    pfn_net = pp.PillarFeatureNet(4, True, (eng.channels,), False, eng.cfg.voxel_size[:], eng.cfg.coors_range[:]).to(dev).eval()
+    pw, pscale, pshift = pp.fold_pfn_layer(pfn_net.pfn_layers[0])
+    pfn_ms = None
+    if eng.channels == 64:
+        for s in range(3):
+            eng.pillar_features(batch(s), pw, pscale, pshift)
+            eng.scatter(eng.read_total_rows())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(args.steps):
+            eng.pillar_features(batch(s), pw, pscale, pshift)
+            eng.scatter(eng.read_total_rows())
+        e1.record()
+        torch.cuda.synchronize()
+        pfn_ms = e0.elapsed_time(e1) / args.steps
+
     # ---- end to end: pinned host points in, BEV u8 + voxel_num back on the host ------------
     from lyft3d_b200.engine import HostPipeline
     pipe = HostPipeline(eng, fused=fused)
@@ -339,7 +359,12 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 points, f64 BEV affine, u32 counts",
                 "data": "synthetic",
                 "config": config_json(F, world, {"mean_pillars_per_frame": round(mean_rows / F, 1), "unfused": not fused}),
-                "roofline": roof, "stages": stage_info, "clocks": clocks, "gpu_launches": int(launches),
+                "roofline": roof, "stages": stage_info,
+                "pillar_path_with_fused_pfn": None if pfn_ms is None else {
+                    "ms_per_step": round(pfn_ms, 4),
+                    "note": "points -> voxelize+decorate+PFNLayer(eval) in one pipeline -> scatter; the unfused "
+                            "chain it replaces is pillarize + a PyTorch PFNLayer + scatter (not part of `value`)"},
+                "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                         "d2h_bytes_per_step": pipe.d2h_bytes,
                         "note": "HostPipeline: pinned host points -> device -> both paths -> BEV u8 + voxel_num "

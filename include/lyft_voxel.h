@@ -231,6 +231,30 @@ int lv_pillarize_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d
                         int32_t* d_num_points, int32_t* d_voxel_num, int64_t* d_voxel_offsets,
                         lv_stream stream);
 
+/* PFNLayer in inference form (second/second/pytorch/models/pointpillars.py:51-65, last layer):
+ * Linear(C_out -> units, weight (units, C_out) row-major, no bias) -> BatchNorm1d in eval mode
+ * folded by the caller to y*scale + shift (scale = gamma/sqrt(var + eps), shift = beta - mean*scale;
+ * scale = 1, shift = bias when the layer has no norm) -> ReLU -> max over the T slots (a padded
+ * slot contributes relu(shift)).  Fused behind the decoration: the (P,T,C_out) tensor of
+ * lv_pillar_decorate is never materialised.  d_out is (P, units) float32;
+ * units in {32, 64, 128}; needs num_features == 4 and max_points <= 64. */
+int lv_pillar_pfn(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,
+                  const int32_t* d_coors, int64_t n_pillars, int32_t max_points, int32_t num_features,
+                  float vx, float vy, float x_offset, float y_offset, int32_t variant,
+                  int32_t with_distance, const float* d_weight, const float* d_scale,
+                  const float* d_shift, int32_t units, float* d_out, lv_stream stream);
+
+/* lv_voxelize_concat + lv_pillar_pfn in one call: points in, (capacity_rows, units) pillar
+ * features out (units == 64), ready for lv_pillar_scatter.  Replaces preprocess.py:299-317 +
+ * :21-55, pointpillars.py:203-231 and :51-65 without writing voxels or decorated points. */
+int lv_pillarize_pfn_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points,
+                            int32_t n_frames, const int64_t* h_frame_offsets, int64_t capacity_rows,
+                            float vx, float vy, float x_offset, float y_offset, int32_t variant,
+                            int32_t with_distance, const float* d_weight, const float* d_scale,
+                            const float* d_shift, int32_t units, float* d_features,
+                            int32_t* d_coords4, int32_t* d_num_points, int32_t* d_voxel_num,
+                            int64_t* d_voxel_offsets, lv_stream stream);
+
 /* lv_pillar_scatter replaces PointPillarsScatter.forward
  * (second/second/pytorch/models/pointpillars.py:444-476):
  * canvas[b, c, y, x] = feats[p, c] for the pillar p with coords[p] = (b, ., y, x),

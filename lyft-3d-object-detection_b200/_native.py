@@ -80,6 +80,11 @@ SIGNATURES = {
     "lv_pillar_out_channels": (ctypes.c_int, [_i32, _i32, _i32]),
     "lv_pillar_decorate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32,
                                           _i32, _i32, _vp, _vp]),
+    "lv_pillar_pfn": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _i32, _i32,
+                                     _vp, _vp, _vp, _i32, _vp, _vp]),
+    "lv_pillarize_pfn_concat": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), _vp, _i32, _vp, _i64, _f32, _f32,
+                                               _f32, _f32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
+                                               _vp, _vp]),
     "lv_pillar_scatter": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lv_voxel_mean": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
 }

@@ -76,11 +76,10 @@ __device__ __forceinline__ void lv_decorate_zero_tail(int num, const DecoCfg& d,
 
 // Decorates the live part of one pillar (T <= 64, C == 4) held in registers by one warp:
 // lane owns slot `lane` (a) and slot `lane + 32` (b); slots >= num must be passed as zeros.
-// The num*C_out floats, laid out [t][C_out], are staged in the warp's shared-memory region
-// `st` and written to `dst` with contiguous (128-bit when aligned) stores.  The caller has
-// already issued lv_decorate_zero_tail for the rest of the row.
-__device__ __forceinline__ void lv_decorate_warp(const float4 a, const float4 b, int num, int coor_y, int coor_x,
-                                                 const DecoCfg& d, float* st, float* __restrict__ dst, int lane) {
+// The live slots land in the warp's shared-memory region `st`, slot t at st + t*slot_stride
+// (C_out for the dense output layout); returns the number of live slots.  Ends with __syncwarp: `st` is readable by every lane.
+__device__ __forceinline__ int lv_decorate_stage(const float4 a, const float4 b, int num, int coor_y, int coor_x,
+                                                 const DecoCfg& d, float* st, int lane, int slot_stride) {
   // mean over ALL T slots, padding zeros included (:208-209)
   const float sx = lv_warp_sum(a.x + b.x), sy = lv_warp_sum(a.y + b.y), sz = lv_warp_sum(a.z + b.z);
   const float fn = (float)num;
@@ -96,19 +95,83 @@ __device__ __forceinline__ void lv_decorate_warp(const float4 a, const float4 b,
   const float cx = __fadd_rn(__fmul_rn((float)coor_x, d.vx), d.x_off);
   const float cy = __fadd_rn(__fmul_rn((float)coor_y, d.vy), d.y_off);
   const int live = lv_live_slots(num, d);
-  if (lane < live) lv_decorate_slot(a, mx, my, mz, cx, cy, height, d, st + lane * d.C_out);
-  if (lane + 32 < live) lv_decorate_slot(b, mx, my, mz, cx, cy, height, d, st + (lane + 32) * d.C_out);
-  const int nd = live * d.C_out;
+  if (lane < live) lv_decorate_slot(a, mx, my, mz, cx, cy, height, d, st + lane * slot_stride);
+  if (lane + 32 < live) lv_decorate_slot(b, mx, my, mz, cx, cy, height, d, st + (lane + 32) * slot_stride);
+  const int nd = live * slot_stride;
+  if (lane < (((nd + 3) >> 2) << 2) - nd) st[nd + lane] = 0.f;  // pad the last quad of the data part
+  __syncwarp();
+  return live;
+}
+
+// lv_decorate_stage + contiguous (128-bit when aligned) stores of the live part to `dst`.  The
+// caller has already issued lv_decorate_zero_tail for the rest of the row.
+__device__ __forceinline__ void lv_decorate_warp(const float4 a, const float4 b, int num, int coor_y, int coor_x,
+                                                 const DecoCfg& d, float* st, float* __restrict__ dst, int lane) {
+  const int nd = lv_decorate_stage(a, b, num, coor_y, coor_x, d, st, lane, d.C_out) * d.C_out;
   if (lv_row_vec4(d, dst)) {
-    const int nd4 = (nd + 3) >> 2;
-    if (lane < (nd4 << 2) - nd) st[nd + lane] = 0.f;  // pad the last quad of the data part
-    __syncwarp();
     const float4* s4 = reinterpret_cast<const float4*>(st);
     float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int i = lane; i < nd4; i += 32) lv_st_stream_f4(d4 + i, s4[i]);
+    for (int i = lane; i < ((nd + 3) >> 2); i += 32) lv_st_stream_f4(d4 + i, s4[i]);
   } else {
-    __syncwarp();
     for (int i = lane; i < nd; i += 32) dst[i] = st[i];
   }
+  __syncwarp();
+}
+
+// ---- PFNLayer (second/second/pytorch/models/pointpillars.py:51-65), inference form, fused
+// behind the decoration: y = W f (Linear 9 -> units, no bias), z = relu(y * scale + shift)
+// (BatchNorm1d in eval mode folded to scale/shift on the host), out = max over the T slots.
+// A padded slot has f = 0, so it contributes relu(shift) to the max whenever live < T.
+#define LV_PFN_MAX_IN 12
+#define LV_PFN_STRIDE 12   // floats per staged slot: three 128-bit broadcast reads fetch a slot
+struct PfnCfg {
+  const float* weight;   // (units, C_in) row-major = torch Linear.weight
+  const float* scale;    // (units)
+  const float* shift;    // (units)
+  int units;             // multiple of 32, <= 128
+};
+
+// lane owns output channels lane + 32 j; its CIN*UJ weights live in registers
+template <int CIN, int UJ>
+struct PfnRegs {
+  float w[CIN][UJ], sc[UJ], sh[UJ];
+  __device__ __forceinline__ void load(const PfnCfg& c, int lane) {
+#pragma unroll
+    for (int j = 0; j < UJ; ++j) {
+      const int ch = lane + 32 * j;
+      sc[j] = __ldg(c.scale + ch);
+      sh[j] = __ldg(c.shift + ch);
+#pragma unroll
+      for (int k = 0; k < CIN; ++k) w[k][j] = __ldg(c.weight + ch * CIN + k);
+    }
+  }
+};
+
+// `st` holds the live slots at stride LV_PFN_STRIDE (16-byte aligned)
+template <int CIN, int UJ>
+__device__ __forceinline__ void lv_pfn_warp(const float* st, int live, int T, const PfnRegs<CIN, UJ>& r,
+                                            float* __restrict__ out, int lane) {
+  float m[UJ];
+#pragma unroll
+  for (int j = 0; j < UJ; ++j) m[j] = live < T ? fmaxf(r.sh[j], 0.f) : 0.f;  // relu >= 0 either way
+  for (int t = 0; t < live; ++t) {
+    const float4* f4 = reinterpret_cast<const float4*>(st + t * LV_PFN_STRIDE);  // broadcast reads
+    float f[LV_PFN_STRIDE];
+    *reinterpret_cast<float4*>(f) = f4[0];
+    *reinterpret_cast<float4*>(f + 4) = f4[1];
+    if (CIN > 8) *reinterpret_cast<float4*>(f + 8) = f4[2];
+    float y[UJ];
+#pragma unroll
+    for (int j = 0; j < UJ; ++j) y[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) {
+#pragma unroll
+      for (int j = 0; j < UJ; ++j) y[j] = fmaf(f[k], r.w[k][j], y[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < UJ; ++j) m[j] = fmaxf(m[j], fmaf(y[j], r.sc[j], r.sh[j]));
+  }
+#pragma unroll
+  for (int j = 0; j < UJ; ++j) out[lane + 32 * j] = m[j];
   __syncwarp();
 }

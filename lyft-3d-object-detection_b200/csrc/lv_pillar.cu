@@ -14,6 +14,8 @@
 //   is written exactly once by a tile kernel (128 cells x C channels per CTA) with
 //   128-bit streaming stores; the memset of the reference is fused away.
 //   Algorithmic bytes: P*(C*4+16) read, B*C*ny*nx*4 written.
+#include <algorithm>
+
 #include "lv_common.cuh"
 #include "lv_decorate.cuh"
 
@@ -128,11 +130,11 @@ __global__ void __launch_bounds__(PIL_WARPS * 32) pillar_decorate_kernel(Decorat
 // Fast path (C == 4, T <= 64): the pillar lives in registers (two float4 per lane), is read
 // exactly once, and leaves through the warp's shared-memory stage as 128-bit stores.
 __global__ void __launch_bounds__(PIL_WARPS * 32, 6) pillar_decorate_fast_kernel(DecorateParams p, DecoCfg d) {
-  extern __shared__ float stage[];  // [PIL_WARPS][T*C_out]
+  extern __shared__ float stage[];  // [PIL_WARPS][T*C_out + 4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = d.T * d.C_out;
   const int64_t warps_total = (int64_t)gridDim.x * PIL_WARPS;
-  float* st = stage + warp * per;
+  float* st = stage + warp * (per + 4);
   for (int64_t pil = (int64_t)blockIdx.x * PIL_WARPS + warp; pil < p.P; pil += warps_total) {
     const float4* v = reinterpret_cast<const float4*>(p.voxels) + pil * d.T;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -143,6 +145,36 @@ __global__ void __launch_bounds__(PIL_WARPS * 32, 6) pillar_decorate_fast_kernel
     const int4 co = __ldg(reinterpret_cast<const int4*>(p.coors) + pil);  // b, z, y, x
     lv_decorate_warp(a, b, num, co.z, co.w, d, st, p.out + pil * per, lane);
   }
+}
+
+// Decoration + PFNLayer (inference) in one pass over (P,T,4) voxels: the (P,T,C_out) decorated
+// tensor is never materialised.  Algorithmic bytes per pillar: T*16 + 20 read, units*4 written.
+template <int CIN, int UJ>
+__global__ void __launch_bounds__(PIL_WARPS * 32) pillar_pfn_kernel(DecorateParams p, DecoCfg d, PfnCfg c) {
+  extern __shared__ __align__(16) float stage[];  // [PIL_WARPS][T * LV_PFN_STRIDE]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * PIL_WARPS;
+  float* st = stage + warp * (d.T * LV_PFN_STRIDE);
+  PfnRegs<CIN, UJ> regs;
+  regs.load(c, lane);
+  for (int64_t pil = (int64_t)blockIdx.x * PIL_WARPS + warp; pil < p.P; pil += warps_total) {
+    const float4* v = reinterpret_cast<const float4*>(p.voxels) + pil * d.T;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (lane < d.T) a = lv_ld_stream_f4(v + lane);
+    if (lane + 32 < d.T) b = lv_ld_stream_f4(v + lane + 32);
+    const int num = __ldg(p.num + pil);
+    const int4 co = __ldg(reinterpret_cast<const int4*>(p.coors) + pil);  // b, z, y, x
+    const int live = lv_decorate_stage(a, b, num, co.z, co.w, d, st, lane, LV_PFN_STRIDE);
+    lv_pfn_warp<CIN, UJ>(st, live, d.T, regs, p.out + pil * c.units, lane);
+  }
+}
+
+template <int CIN>
+static void pillar_pfn_launch(int units, unsigned blocks, size_t smem, cudaStream_t stream, const DecorateParams& p,
+                              const DecoCfg& d, const PfnCfg& c) {
+  if (units == 32) pillar_pfn_kernel<CIN, 1><<<blocks, PIL_WARPS * 32, smem, stream>>>(p, d, c);
+  else if (units == 64) pillar_pfn_kernel<CIN, 2><<<blocks, PIL_WARPS * 32, smem, stream>>>(p, d, c);
+  else pillar_pfn_kernel<CIN, 4><<<blocks, PIL_WARPS * 32, smem, stream>>>(p, d, c);
 }
 
 // ---------------------------------------------------------------- scatter
@@ -262,7 +294,7 @@ extern "C" int lv_pillar_decorate(lv_handle* h, const float* d_voxels, const int
   LV_CHECK_CUDA(cudaSetDevice(h->device));
   DecorateParams p{d_voxels, d_num_points, d_coors, n_pillars, max_points, num_features, c_out,
                    vx, vy, x_offset, y_offset, variant, with_distance ? 1 : 0, d_out};
-  const size_t smem = (size_t)PIL_WARPS * max_points * c_out * sizeof(float);
+  const size_t smem = (size_t)PIL_WARPS * (max_points * c_out + 4) * sizeof(float);
   LV_REQUIRE(smem <= 200 * 1024, "lv_pillar_decorate: max_points*channels too large for the shared-memory stage");
   const int64_t grid = lv_div_up(n_pillars, PIL_WARPS);
   LV_REQUIRE(grid < (1ll << 31), "lv_pillar_decorate: too many pillars");
@@ -284,6 +316,36 @@ extern "C" int lv_pillar_decorate(lv_handle* h, const float* d_voxels, const int
       LV_CHECK_CUDA(cudaFuncSetAttribute(pillar_decorate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pillar_decorate_kernel<false><<<(unsigned)grid, PIL_WARPS * 32, smem, stream>>>(p);
   }
+  LV_LAUNCH_CHECK(h);
+  return LV_OK;
+}
+
+extern "C" int lv_pillar_pfn(lv_handle* h, const float* d_voxels, const int32_t* d_num_points, const int32_t* d_coors,
+                             int64_t n_pillars, int32_t max_points, int32_t num_features, float vx, float vy,
+                             float x_offset, float y_offset, int32_t variant, int32_t with_distance,
+                             const float* d_weight, const float* d_scale, const float* d_shift, int32_t units,
+                             float* d_out, lv_stream stream_) {
+  LV_REQUIRE(h != nullptr, "lv_pillar_pfn: null handle");
+  LV_REQUIRE(n_pillars >= 0 && max_points > 0 && max_points <= 64 && num_features == 4,
+             "lv_pillar_pfn: needs 4 features per point and max_points <= 64 (got %d, %d)", num_features, max_points);
+  const int c_out = lv_pillar_out_channels(num_features, variant, with_distance);
+  LV_REQUIRE(c_out >= 8 && c_out <= 10, "lv_pillar_pfn: bad variant %d", variant);
+  LV_REQUIRE(units == 32 || units == 64 || units == 128, "lv_pillar_pfn: units must be 32, 64 or 128, got %d", units);
+  if (n_pillars == 0) return LV_OK;
+  LV_REQUIRE(d_voxels && d_num_points && d_coors && d_weight && d_scale && d_shift && d_out, "lv_pillar_pfn: null pointer");
+  LV_REQUIRE((reinterpret_cast<uintptr_t>(d_coors) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_voxels) & 15) == 0,
+             "lv_pillar_pfn: voxels and coors must be 16-byte aligned");
+  LV_CHECK_CUDA(cudaSetDevice(h->device));
+  DecorateParams p{d_voxels, d_num_points, d_coors, n_pillars, max_points, num_features, c_out,
+                   vx, vy, x_offset, y_offset, variant, with_distance ? 1 : 0, d_out};
+  DecoCfg d{vx, vy, x_offset, y_offset, variant, with_distance ? 1 : 0, max_points, c_out};
+  PfnCfg c{d_weight, d_scale, d_shift, units};
+  const size_t smem = (size_t)PIL_WARPS * max_points * LV_PFN_STRIDE * sizeof(float);   // <= 24 KB
+  const unsigned blocks = (unsigned)std::min<int64_t>((int64_t)h->num_sms * 8, lv_div_up(n_pillars, PIL_WARPS));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (c_out == 8) pillar_pfn_launch<8>(units, blocks, smem, stream, p, d, c);        // radius
+  else if (c_out == 9) pillar_pfn_launch<9>(units, blocks, smem, stream, p, d, c);   // pfn, old, radius_height, radius+distance
+  else pillar_pfn_launch<10>(units, blocks, smem, stream, p, d, c);                  // +distance
   LV_LAUNCH_CHECK(h);
   return LV_OK;
 }

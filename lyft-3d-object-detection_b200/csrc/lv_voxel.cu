@@ -61,6 +61,7 @@ struct VoxParams {
   int64_t pt_lo;               // first point of the sub-batch (global point index)
   float lo[3], vs[3];
   int grid[3];                 // gx, gy, gz
+  unsigned row_div_m;          // ceil(2^32 / T): voxel of a flat slot index < 2^20
   unsigned div_m[2];           // exact division of a cell id (< 2^28) by gx*gy [0] and by gx [1]:
   int div_s[2];                //   q = (n * m) >> s   (vx_make_div)
   int64_t G;                   // cells per frame
@@ -451,8 +452,13 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p) {
 // ---------------------------------------------------------------- K6: bins -> output rows
 // grid = (n_bins, frames).  Shared memory: slot table [2^L][T] of point indices, running
 // per-voxel counts [2^L], per-warp tile counters [8][2^L], (fused) decoration stage.
-template <bool DECO, bool C4>
-__global__ void __launch_bounds__(VX_THREADS, 4) vx_bins_kernel(VoxParams p, DecoCfg d, float* __restrict__ decorated) {
+#define VX_OUT_VOXELS 0     // raw (T,C) voxels
+#define VX_OUT_DECORATE 1   // PillarFeatureNet decoration fused into the gather, one warp per pillar
+#define VX_OUT_PFN 2        // decoration + PFNLayer (inference) fused into the gather: (rows, units) features
+template <int MODE, bool C4>
+__global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bins_kernel(VoxParams p, DecoCfg d, float* __restrict__ decorated,
+                                                                PfnCfg pfn) {
+  constexpr bool DECO = MODE != VX_OUT_VOXELS;
   extern __shared__ __align__(16) int smem[];
   const int NV = 1 << p.low_bits;
   int* slot_tab = smem;                    // [NV][T]
@@ -560,13 +566,51 @@ __global__ void __launch_bounds__(VX_THREADS, 4) vx_bins_kernel(VoxParams p, Dec
     __syncthreads();
   }
   __syncthreads();
-  // ---- phase 2: one (sub)warp per voxel writes the output row ----
+  // ---- phase 2: the output rows of the bin (contiguous in memory) ----
   const long long row0 = s_row0;
   const int32_t* ccell = p.creator_cell + (fstart - p.pt_lo);
+  if (row0 + v0 + nv > p.capacity) nv = (int)(p.capacity - (row0 + v0) > 0 ? p.capacity - (row0 + v0) : 0);
+  if (MODE == VX_OUT_VOXELS && C4) {
+    // 2a: one thread per voxel: count and coordinates
+    const float4* pts4 = reinterpret_cast<const float4*>(p.pts) + fstart;
+    for (int v = threadIdx.x; v < nv; v += VX_THREADS) {
+      int n = total[v];
+      if (n > p.T) n = p.T;
+      total[v] = n;
+      const long long row = row0 + v0 + v;
+      int cx, cy, cz;
+      vx_cell_coords(p, ccell[v0 + v], cz, cy, cx);
+      p.num_points[row] = n;
+      if (p.coord_cols == 4) {
+        *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(f, cz, cy, cx);  // preprocess.py:44-50
+      } else {
+        int32_t* co = p.coords + row * 3;
+        co[0] = cz; co[1] = cy; co[2] = cx;  // reversed (z,y,x), simplevis.py:42
+      }
+    }
+    __syncthreads();
+    // 2b: the whole CTA streams the rows of the bin as one flat array of float4 (one per slot):
+    //     live slots gather their point, padding slots are zeros from registers
+    float4* out4 = reinterpret_cast<float4*>(p.voxels) + (row0 + v0) * p.T;
+    const int total4 = nv * p.T;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int j = threadIdx.x; j < total4; j += VX_THREADS) {
+      const int v = (int)(((unsigned long long)(unsigned)j * p.row_div_m) >> 32);   // j / T (j < 2^20)
+      const int r = j - v * p.T;
+      float4 o = z4;
+      if (r < total[v]) o = __ldg(pts4 + slot_tab[v * p.T + r]);
+      lv_st_stream_f4(out4 + j, o);
+    }
+    return;
+  }
   if (DECO) {
     const int per = d.T * d.C_out;
-    float* st = stage + warp * per;
+    // per-warp stage: the dense (T, C_out) row (+ pad), or T slots at stride LV_PFN_STRIDE
+    float* st = stage + warp * (MODE == VX_OUT_PFN ? d.T * LV_PFN_STRIDE : per + 4);
     const float4* pts4 = reinterpret_cast<const float4*>(p.pts) + fstart;
+    PfnRegs<9, 2> pfn_regs;   // the fused path serves the PointPillars PFN: 9 inputs, 64 units
+    if (MODE == VX_OUT_PFN) pfn_regs.load(pfn, lane);
     // two pillars per iteration: the point gathers of both are in flight, and the zero part
     // of both rows is already streaming out, before either gather is consumed
     for (int v = warp * 2; v < nv; v += VX_WARPS * 2) {
@@ -585,8 +629,10 @@ __global__ void __launch_bounds__(VX_THREADS, 4) vx_bins_kernel(VoxParams p, Dec
       if (lane + 32 < n1) b1 = __ldg(pts4 + sl[p.T + lane + 32]);
       const int c0 = ccell[v0 + v], c1 = two ? ccell[v0 + v + 1] : 0;
       float* dst0 = decorated + row * per;
-      lv_decorate_zero_tail(n0, d, dst0, lane);
-      if (two) lv_decorate_zero_tail(n1, d, dst0 + per, lane);
+      if (MODE == VX_OUT_DECORATE) {
+        lv_decorate_zero_tail(n0, d, dst0, lane);
+        if (two) lv_decorate_zero_tail(n1, d, dst0 + per, lane);
+      }
       int cx0, cy0, cz0, cx1, cy1, cz1;
       vx_cell_coords(p, c0, cz0, cy0, cx0);
       vx_cell_coords(p, c1, cz1, cy1, cx1);
@@ -598,8 +644,18 @@ __global__ void __launch_bounds__(VX_THREADS, 4) vx_bins_kernel(VoxParams p, Dec
           *reinterpret_cast<int4*>(p.coords + (row + 1) * 4) = make_int4(f, cz1, cy1, cx1);
         }
       }
-      lv_decorate_warp(a0, b0, n0, cy0, cx0, d, st, dst0, lane);
-      if (two) lv_decorate_warp(a1, b1, n1, cy1, cx1, d, st, dst0 + per, lane);
+      if (MODE == VX_OUT_DECORATE) {
+        lv_decorate_warp(a0, b0, n0, cy0, cx0, d, st, dst0, lane);
+        if (two) lv_decorate_warp(a1, b1, n1, cy1, cx1, d, st, dst0 + per, lane);
+      } else {  // VX_OUT_PFN: `decorated` is the (rows, units) feature matrix
+        float* f0 = decorated + row * pfn.units;
+        int live = lv_decorate_stage(a0, b0, n0, cy0, cx0, d, st, lane, LV_PFN_STRIDE);
+        lv_pfn_warp<9, 2>(st, live, d.T, pfn_regs, f0, lane);
+        if (two) {
+          live = lv_decorate_stage(a1, b1, n1, cy1, cx1, d, st, lane, LV_PFN_STRIDE);
+          lv_pfn_warp<9, 2>(st, live, d.T, pfn_regs, f0 + pfn.units, lane);
+        }
+      }
     }
   } else {
     // LPV lanes per voxel: 32 for pillars, 8 for T <= 8
@@ -684,7 +740,7 @@ static int vx_set_smem(K kernel, size_t bytes) {
 static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
                   const int64_t* h_frame_offsets, float* d_voxels, int32_t* d_coords, int32_t* d_num_points,
                   int32_t* d_voxel_num, int concat, int64_t capacity, int64_t* d_row_base, const DecoCfg* deco,
-                  float* d_decorated, lv_stream stream_) {
+                  float* d_decorated, const PfnCfg* pfn, lv_stream stream_) {
   LV_REQUIRE(h != nullptr, "lv_voxelize: null handle");
   LV_REQUIRE(cfg && h_frame_offsets, "lv_voxelize: null config / frame offsets");
   LV_REQUIRE(n_frames >= 0, "lv_voxelize: negative frame count");
@@ -712,10 +768,12 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   while ((((int64_t)V + (1 << L) - 1) >> L) > VX_MAX_BINS && L < 20) ++L;
   const int n_bins = (int)(((int64_t)V + (1 << L) - 1) >> L);
   const int NV = 1 << L;
-  const size_t deco_stage = deco ? (size_t)VX_WARPS * T * deco->C_out * 4 : 0;
+  const size_t deco_stage = pfn ? (size_t)VX_WARPS * T * LV_PFN_STRIDE * 4
+                                 : (deco ? (size_t)VX_WARPS * (T * deco->C_out + 4) * 4 : 0);
   const size_t smem_bins = ((size_t)NV * T + NV + (size_t)VX_WARPS * NV) * 4 + deco_stage;
   LV_REQUIRE(smem_bins <= 220 * 1024, "lv_voxelize: max_points %d x max_voxels %d needs %zu bytes of shared memory "
              "per bin (limit 220 KB)", T, V, smem_bins);
+  LV_REQUIRE((int64_t)NV * T < (1ll << 20), "lv_voxelize: bin of %d voxels x %d points is too large", NV, T);
   const size_t smem_scatter = (size_t)VX_WARPS * n_bins * 4;
   const size_t smem_keys = (size_t)n_bins * 4;
 
@@ -781,6 +839,9 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   DecoCfg dcfg;
   memset(&dcfg, 0, sizeof(dcfg));
   if (deco) dcfg = *deco;
+  PfnCfg pcfg;
+  memset(&pcfg, 0, sizeof(pcfg));
+  if (pfn) pcfg = *pfn;
 
   // K1 stages full chunks by TMA when a chunk of rows is a multiple of 16 bytes and fits 64 KB
   p.tma_bytes = 0;
@@ -789,9 +850,11 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   else LV_CHECK(vx_set_smem(vx_cells_kernel<false>, p.tma_bytes));
   LV_CHECK(vx_set_smem(vx_keys_kernel, smem_keys));
   LV_CHECK(vx_set_smem(vx_scatter_kernel, smem_scatter));
-  if (deco) LV_CHECK(vx_set_smem(vx_bins_kernel<true, true>, smem_bins));
-  else if (out4) LV_CHECK(vx_set_smem(vx_bins_kernel<false, true>, smem_bins));
-  else LV_CHECK(vx_set_smem(vx_bins_kernel<false, false>, smem_bins));
+  if (pfn) LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_PFN, true>, smem_bins));
+  else if (deco) LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_DECORATE, true>, smem_bins));
+  else if (out4) LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_VOXELS, true>, smem_bins));
+  else LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_VOXELS, false>, smem_bins));
+  p.row_div_m = (unsigned)(((1ull << 32) + (uint32_t)T - 1) / (uint32_t)T);
 
   int f0 = 0;
   while (f0 < n_frames) {
@@ -838,9 +901,10 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     }
     {
       dim3 grid_b((unsigned)n_bins, (unsigned)nf);
-      if (deco) vx_bins_kernel<true, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, d_decorated);
-      else if (out4) vx_bins_kernel<false, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, nullptr);
-      else vx_bins_kernel<false, false><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, nullptr);
+      if (pfn) vx_bins_kernel<VX_OUT_PFN, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, d_decorated, pcfg);
+      else if (deco) vx_bins_kernel<VX_OUT_DECORATE, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, d_decorated, pcfg);
+      else if (out4) vx_bins_kernel<VX_OUT_VOXELS, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, nullptr, pcfg);
+      else vx_bins_kernel<VX_OUT_VOXELS, false><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, nullptr, pcfg);
       LV_LAUNCH_CHECK(h);
     }
     if (!concat && cfg->zero_tail) {
@@ -858,7 +922,7 @@ extern "C" int lv_voxelize(lv_handle* h, const lv_voxel_config* cfg, const float
                            const int64_t* h_frame_offsets, float* d_voxels, int32_t* d_coords, int32_t* d_num_points,
                            int32_t* d_voxel_num, lv_stream stream) {
   return vx_run(h, cfg, d_points, n_frames, h_frame_offsets, d_voxels, d_coords, d_num_points, d_voxel_num, 0, 0,
-                nullptr, nullptr, nullptr, stream);
+                nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int lv_voxelize_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
@@ -868,7 +932,7 @@ extern "C" int lv_voxelize_concat(lv_handle* h, const lv_voxel_config* cfg, cons
   LV_REQUIRE(capacity_rows >= 0, "lv_voxelize_concat: negative capacity");
   LV_REQUIRE(n_frames == 0 || d_voxel_offsets, "lv_voxelize_concat: null voxel_offsets");
   return vx_run(h, cfg, d_points, n_frames, h_frame_offsets, d_voxels, d_coords4, d_num_points, d_voxel_num, 1,
-                capacity_rows, d_voxel_offsets, nullptr, nullptr, stream);
+                capacity_rows, d_voxel_offsets, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int lv_pillarize_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
@@ -883,7 +947,27 @@ extern "C" int lv_pillarize_concat(lv_handle* h, const lv_voxel_config* cfg, con
   LV_REQUIRE(c_out > 0, "lv_pillarize_concat: bad variant %d", variant);
   DecoCfg d{vx, vy, x_offset, y_offset, variant, with_distance ? 1 : 0, cfg->max_points, c_out};
   return vx_run(h, cfg, d_points, n_frames, h_frame_offsets, nullptr, d_coords4, d_num_points, d_voxel_num, 1,
-                capacity_rows, d_voxel_offsets, &d, d_decorated, stream);
+                capacity_rows, d_voxel_offsets, &d, d_decorated, nullptr, stream);
+}
+
+extern "C" int lv_pillarize_pfn_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
+                                       const int64_t* h_frame_offsets, int64_t capacity_rows, float vx, float vy,
+                                       float x_offset, float y_offset, int32_t variant, int32_t with_distance,
+                                       const float* d_weight, const float* d_scale, const float* d_shift, int32_t units,
+                                       float* d_features, int32_t* d_coords4, int32_t* d_num_points,
+                                       int32_t* d_voxel_num, int64_t* d_voxel_offsets, lv_stream stream) {
+  LV_REQUIRE(cfg != nullptr, "lv_pillarize_pfn_concat: null config");
+  LV_REQUIRE(capacity_rows >= 0, "lv_pillarize_pfn_concat: negative capacity");
+  LV_REQUIRE(n_frames == 0 || d_voxel_offsets, "lv_pillarize_pfn_concat: null voxel_offsets");
+  const int c_out = lv_pillar_out_channels(cfg->num_features, variant, with_distance);
+  LV_REQUIRE(c_out == 9, "lv_pillarize_pfn_concat: the fused path needs a 9-channel decoration (variant %d, "
+             "with_distance %d gives %d)", variant, with_distance, c_out);
+  LV_REQUIRE(units == 64, "lv_pillarize_pfn_concat: units must be 64 (the PointPillars PFN width), got %d", units);
+  LV_REQUIRE(d_weight && d_scale && d_shift, "lv_pillarize_pfn_concat: null PFN parameters");
+  DecoCfg d{vx, vy, x_offset, y_offset, variant, with_distance ? 1 : 0, cfg->max_points, c_out};
+  PfnCfg c{d_weight, d_scale, d_shift, units};
+  return vx_run(h, cfg, d_points, n_frames, h_frame_offsets, nullptr, d_coords4, d_num_points, d_voxel_num, 1,
+                capacity_rows, d_voxel_offsets, &d, d_features, &c, stream);
 }
 
 extern "C" int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const float* h_points, int32_t n_frames,

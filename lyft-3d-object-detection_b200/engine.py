@@ -101,6 +101,17 @@ class FrameBatchEngine:
             self.vx, self.vy, self.x_off, self.y_off, 0, 0, self.decorated.data_ptr(), self.coords.data_ptr(),
             self.num_points.data_ptr(), self.voxel_num.data_ptr(), self.voxel_offsets.data_ptr(), st))
 
+    def pillar_features(self, points, weight, scale, shift):
+        """voxelize + decorate + last PFNLayer (eval) fused (lv_pillarize_pfn_concat): points in,
+        (rows, 64) pillar features in ``self.features`` - neither the voxels nor the decorated
+        points are written.  weight/scale/shift come from pointpillars.fold_pfn_layer."""
+        st = nat.current_stream_ptr(self.dev)
+        nat.check(self.lib.lv_pillarize_pfn_concat(
+            self.h.ptr, ctypes.byref(self.cfg), points.data_ptr(), self.F, self.offsets.ctypes.data, self.cap,
+            self.vx, self.vy, self.x_off, self.y_off, 0, 0, weight.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+            int(weight.shape[0]), self.features.data_ptr(), self.coords.data_ptr(), self.num_points.data_ptr(),
+            self.voxel_num.data_ptr(), self.voxel_offsets.data_ptr(), st))
+
     def read_total_rows(self):
         """The one host read of the pillar path: total pillars of the batch (the
         reference keeps num_voxels on the host too, preprocess.py:310)."""

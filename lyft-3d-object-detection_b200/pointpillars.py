@@ -8,8 +8,10 @@ checkpoints load and ``module_class_name`` in a config resolves unchanged.
 
   PillarFeatureNet / ...Old / ...Radius / ...RadiusHeight
       decoration (mean offset, pillar-centre offset, padding mask, variants) is ONE
-      fused CUDA kernel (lv_pillar_decorate); the PFNLayer (Linear 9->64 + BN +
-      ReLU + max) stays in PyTorch exactly as in the reference.
+      fused CUDA kernel (lv_pillar_decorate).  In training the PFNLayer (Linear 9->64 +
+      BN + ReLU + max) stays in PyTorch exactly as in the reference (batch statistics,
+      autograd); in eval mode a single-layer net runs decoration + PFNLayer as ONE kernel
+      (lv_pillar_pfn) and the (P,T,9) tensor is never written.
   PointPillarsScatter
       scatter-as-gather CUDA kernel (lv_pillar_scatter), differentiable w.r.t.
       ``voxel_features`` (the backward is a torch gather of the canvas gradient).
@@ -103,6 +105,47 @@ def decorate_pillars(features, num_voxels, coors, vx, vy, x_offset, y_offset, va
     return out
 
 
+def fold_pfn_layer(layer):
+    """(weight, scale, shift) float32 CUDA tensors of a last PFNLayer in eval mode:
+    relu(BN(Wx)) == relu((Wx) * scale + shift) (pointpillars.py:51-62)."""
+    w = layer.linear.weight.detach().float().contiguous()
+    if isinstance(layer.norm, nn.BatchNorm1d):
+        bn = layer.norm
+        inv = torch.rsqrt(bn.running_var.detach().double() + bn.eps)
+        g = bn.weight.detach().double() if bn.affine else torch.ones_like(inv)
+        b = bn.bias.detach().double() if bn.affine else torch.zeros_like(inv)
+        scale = g * inv
+        shift = b - bn.running_mean.detach().double() * scale
+        if layer.linear.bias is not None:
+            shift = shift + layer.linear.bias.detach().double() * scale
+    else:
+        scale = torch.ones(w.shape[0], dtype=torch.float64, device=w.device)
+        shift = (layer.linear.bias.detach().double() if layer.linear.bias is not None
+                 else torch.zeros(w.shape[0], dtype=torch.float64, device=w.device))
+    return w, scale.float().contiguous(), shift.float().contiguous()
+
+
+def pillar_pfn(features, num_voxels, coors, vx, vy, x_offset, y_offset, weight, scale, shift, variant="pfn",
+               with_distance=False):
+    """Decoration + last PFNLayer (eval) fused: (P,T,4) float32 -> (P,units) float32."""
+    _require_cuda_f32(features, "features")
+    lib = nat.load()
+    features = features.contiguous()
+    P, T, C = features.shape
+    num = num_voxels.to(torch.int32).contiguous()
+    co = coors.to(torch.int32).contiguous()
+    units = weight.shape[0]
+    out = torch.empty((P, units), dtype=torch.float32, device=features.device)
+    h = nat.get_handle(features.device.index)
+    with torch.cuda.device(features.device):
+        nat.check(lib.lv_pillar_pfn(h.ptr, features.data_ptr(), num.data_ptr(), co.data_ptr(), P, T, C,
+                                    _f32(vx), _f32(vy), _f32(x_offset), _f32(y_offset),
+                                    nat.PILLAR_VARIANTS[variant], int(bool(with_distance)), weight.data_ptr(),
+                                    scale.data_ptr(), shift.data_ptr(), units, out.data_ptr(),
+                                    nat.current_stream_ptr(features.device)))
+    return out
+
+
 class PFNLayer(nn.Module):
     """pointpillars.py:17-65 - unchanged PyTorch layer (Linear, BatchNorm1d eps=1e-3
     momentum=0.01, ReLU, max over the points of a pillar)."""
@@ -157,7 +200,23 @@ class _PillarFeatureNetBase(nn.Module):
         return decorate_pillars(features, num_voxels, coors, self.vx, self.vy, self.x_offset, self.y_offset,
                                 variant=self._variant, with_distance=self._with_distance)
 
+    def can_fuse(self, features):
+        """The fused kernel is inference-only: eval mode, one PFNLayer, 4 input features,
+        <= 64 points per pillar, 32/64/128 units, and nothing that needs a gradient."""
+        if self.training or len(self.pfn_layers) != 1:
+            return False
+        layer = self.pfn_layers[0]
+        if features.dim() != 3 or features.shape[2] != 4 or features.shape[1] > 64 or layer.units not in (32, 64, 128):
+            return False
+        needs_grad = features.requires_grad or any(q.requires_grad for q in layer.parameters())
+        return not (torch.is_grad_enabled() and needs_grad)
+
     def forward(self, features, num_voxels, coors):
+        if self.can_fuse(features):
+            w, scale, shift = fold_pfn_layer(self.pfn_layers[0])
+            out = pillar_pfn(features, num_voxels, coors, self.vx, self.vy, self.x_offset, self.y_offset, w, scale,
+                             shift, variant=self._variant, with_distance=self._with_distance)
+            return out.squeeze()
         features = self.decorate(features, num_voxels, coors)
         for pfn in self.pfn_layers:
             features = pfn(features)
