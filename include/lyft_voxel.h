@@ -130,6 +130,29 @@ int lv_bev_normalize(lv_handle* h, const float* d_in, int64_t n, float max_inten
 int lv_transform_points(lv_handle* h, const float* d_points, int32_t point_stride, int64_t n,
                         const double* h_tm16, double* d_out, lv_stream stream);
 
+/* ------------------------------------------------------------------ multi-sweep ingest
+ *
+ * The step in front of VoxelGenerator.generate: n_sweeps raw sweeps (5 float32 per point:
+ * x, y, z, intensity, ring - LidarPointCloud.from_file, data_classes.py:269-284), back to back in
+ * d_raw, become one cloud in the key frame.
+ *   LV_INGEST_SECOND  second/second/data/nuscenes_dataset.py:196-223: intensity /= 255; sweeps with a
+ *     transform: xyz = xyz @ R.T (float64, stored to float32) then xyz += T (float64, stored to
+ *     float32); column 4 := time lag.  out_cols 4 -> [x,y,z,lag] (the reference's column select
+ *     [0,1,2,4]), 5 -> [x,y,z,intensity/255,lag].
+ *   LV_INGEST_DEVKIT  lyft_dataset_sdk/utils/data_classes.py:99-137: xyz = (M . [x;y;z;1])[:3] in
+ *     float64, stored once; remove_close(close_radius) turns rows with |x| < r and |y| < r into NaN
+ *     rows (dropped by every downstream kernel; close_radius < 0 disables it).  out_cols 4 ->
+ *     [x,y,z,intensity], 5 -> [.., time lag].
+ * h_sweep_tm: n_sweeps row-major float64 4x4 (SECOND reads R = [:3,:3], T = [:3,3]); NULL = no
+ * transform at all.  h_has_tm: NULL or n_sweeps flags (0 = leave the sweep untouched, as the
+ * reference does for the key sweep).  h_time_lag: n_sweeps float32 (ts - sweep_ts). */
+#define LV_INGEST_SECOND 0
+#define LV_INGEST_DEVKIT 1
+int lv_ingest_sweeps(lv_handle* h, const float* d_raw, int32_t n_sweeps,
+                     const int64_t* h_sweep_offsets, const double* h_sweep_tm,
+                     const uint8_t* h_has_tm, const float* h_time_lag, int32_t mode,
+                     float close_radius, int32_t out_cols, float* d_out, lv_stream stream);
+
 /* ------------------------------------------------------------------ hard voxelizer
  *
  * Replaces spconv.utils.VoxelGeneratorV2.generate / generate_multi_gpu as called at

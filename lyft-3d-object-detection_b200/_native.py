@@ -70,6 +70,7 @@ SIGNATURES = {
                                              _vp, _vp, _vp, _vp, _vp]),
     "lv_bev_normalize": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, _vp]),
     "lv_transform_points": (ctypes.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "lv_ingest_sweeps": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32, _vp, _vp]),
     "lv_voxel_grid_size": (ctypes.c_int, [ctypes.POINTER(VoxelConfig), _vp]),
     "lv_voxelize": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lv_voxelize_concat": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp,

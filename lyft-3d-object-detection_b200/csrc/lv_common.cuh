@@ -90,6 +90,9 @@ struct lv_handle {
 
   // pillar
   lv_buffer pil_map;                  // i32 [B][ny*nx]
+
+  // multi-sweep ingest
+  lv_mirror ing_offsets, ing_tm, ing_lag, ing_has;
 };
 
 // every device buffer a handle owns (for lv_destroy / lv_workspace_bytes)
@@ -99,7 +102,8 @@ inline std::vector<lv_buffer*> lv_all_buffers(lv_handle* h) {
           &h->bev_stage_map, &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1], &h->vox_vals[0],
           &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state, &h->vox_row_base,
           &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_stage_points, &h->vox_stage_out[0],
-          &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3], &h->pil_map};
+          &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3], &h->pil_map, &h->ing_offsets.dev,
+          &h->ing_tm.dev, &h->ing_lag.dev, &h->ing_has.dev};
 }
 
 inline size_t lv_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

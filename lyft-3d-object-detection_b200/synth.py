@@ -117,3 +117,31 @@ def map_raster(shape_hw=(1024, 1024), seed=4000, blobs=40):
         ch = int(rng.integers(0, 3))
         m[y0:y0 + dy, x0:x0 + dx, ch] = 255
     return m
+
+
+def ingest_case(n_sweeps=4, n_key=6000, seed=77):
+    """Seeded multi-sweep case for the ingest path: slices of the bundled
+    sweep as raw (M,5) rows, a full 3-D rotation + translation per sweep (float64) and
+    microsecond timestamps - the fields of the reference's info["sweeps"] entries."""
+    rng = np.random.default_rng(seed)
+    raw = load_fixture_raw()
+    raw = raw.copy()
+    raw[::50, :2] *= 0.01          # a few returns close to the sensor (exercise remove_close)
+    key = np.ascontiguousarray(raw[:n_key])
+    ts_us = 1_550_000_000_000_000
+    sweeps = []
+    at = n_key
+    for s in range(n_sweeps):
+        m = 3000 + 517 * s
+        ang = rng.normal(size=3) * 0.05
+        cx, cy, cz = np.cos(ang)
+        sx, sy, sz = np.sin(ang)
+        rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        sweeps.append({"points": np.ascontiguousarray(raw[at:at + m]),
+                       "sweep2lidar_rotation": rz @ ry @ rx,
+                       "sweep2lidar_translation": rng.normal(size=3) * np.array([2.0, 0.5, 0.05]),
+                       "timestamp": ts_us - 50_000 * (s + 1)})
+        at += m
+    return key, sweeps, ts_us

@@ -82,3 +82,49 @@ def load_simplevis():
         core.box_np_ops = _shell("second.core.box_np_ops")  # only used by drawing helpers
     return _exec("second.utils.simplevis_ref",
                  os.path.join(REF, "second", "second", "utils", "simplevis.py"))
+
+
+def load_devkit_data_classes():
+    """Returns the reference's nuscenes-devkit/lyft_dataset_sdk/utils/data_classes.py module
+    (LidarPointCloud.from_file / transform / remove_close).  pyquaternion is absent here and
+    only needed by code paths that build matrices from quaternions, so it gets an empty shell;
+    geometry_utils is executed from the reference too."""
+    pq = _shell("pyquaternion")
+    if not hasattr(pq, "Quaternion"):
+        class Quaternion:  # only built as a default argument on the paths used
+            def __init__(self, *a, **k):
+                pass
+        pq.Quaternion = Quaternion
+    if "matplotlib" not in sys.modules:      # type annotations only (matplotlib.axes.Axes)
+        try:
+            import matplotlib  # noqa: F401
+        except ImportError:
+            _shell("matplotlib")
+            ax = _shell("matplotlib.axes")
+            ax.Axes = object
+    _shell("lyft_dataset_sdk")
+    _shell("lyft_dataset_sdk.utils")
+    base = os.path.join(REF, "nuscenes-devkit", "lyft_dataset_sdk", "utils")
+    _exec("lyft_dataset_sdk.utils.geometry_utils", os.path.join(base, "geometry_utils.py"))
+    return _exec("lyft_dataset_sdk.utils.data_classes", os.path.join(base, "data_classes.py"))
+
+
+def run_second_get_sensor_points(info):
+    """Executes the point-assembly statements of the reference's
+    NuScenesDataset.get_sensor_data (second/second/data/nuscenes_dataset.py:196-223) on `info`
+    (a dict with lidar_path, timestamp, sweeps[...] as the reference's info pickles hold) and
+    returns its `points`.  The module itself cannot be imported (spconv, fire); the statements
+    are read from the reference file at run time and executed unchanged."""
+    import textwrap
+    from pathlib import Path
+
+    import numpy as np
+    path = os.path.join(REF, "second", "second", "data", "nuscenes_dataset.py")
+    with open(path) as f:
+        lines = f.readlines()
+    start = next(i for i, l in enumerate(lines) if "lidar_path = Path(info['lidar_path'])" in l)
+    end = next(i for i, l in enumerate(lines) if "axis=0)[:, [0, 1, 2, 4]]" in l)
+    src = textwrap.dedent("".join(lines[start:end + 1]))
+    ns = {"np": np, "Path": Path, "info": info}
+    exec(compile(src, path, "exec"), ns)
+    return ns["points"]
