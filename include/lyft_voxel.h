@@ -211,6 +211,17 @@ int lv_voxelize_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_
                        float* d_voxels, int32_t* d_coords4, int32_t* d_num_points,
                        int32_t* d_voxel_num, int64_t* d_voxel_offsets, lv_stream stream);
 
+/* The un-padding VoxelNet.forward does for multi-GPU batches
+ * (second/second/pytorch/models/voxelnet.py:346-358): padded (B,V,T,C) voxels, (B,V) num_points,
+ * (B,V,coor_cols) coordinates (merge_second_batch_multigpu, preprocess.py:60-88) and num_voxels (B)
+ * become the concatenated (sum, T, C) / (sum) / (sum, coor_cols) lists; *d_out_total = sum.
+ * Outputs need room for B*V rows (or the known total). */
+int lv_unpad_batch(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,
+                   const int32_t* d_coors, const int32_t* d_num_voxels, int32_t batch_size,
+                   int32_t max_voxels, int32_t max_points, int32_t num_features, int32_t coor_cols,
+                   float* d_out_voxels, int32_t* d_out_num_points, int32_t* d_out_coors,
+                   int64_t* d_out_total, lv_stream stream);
+
 int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const float* h_points,
                      int32_t n_frames, const int64_t* h_frame_offsets, float* h_voxels,
                      int32_t* h_coords, int32_t* h_num_points, int32_t* h_voxel_num);

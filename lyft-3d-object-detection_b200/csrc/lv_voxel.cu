@@ -711,6 +711,49 @@ __global__ void __launch_bounds__(VX_THREADS) vx_zero_tail_kernel(VoxParams p) {
   }
 }
 
+// ---------------------------------------------------------------- multi-GPU batch un-padding
+// VoxelNet.forward (second/second/pytorch/models/voxelnet.py:346-358): a padded batch
+// (B,V,T,C) / (B,V) / (B,V,4) + num_voxels (B) becomes the concatenated lists the network
+// consumes.  grid = (row blocks, B); every CTA derives its sample's first output row from the
+// counts of the samples before it.  Rows are copied as float4 when T*C % 4 == 0.
+__global__ void __launch_bounds__(256) vx_unpad_kernel(const float* __restrict__ voxels, const int32_t* __restrict__ num_points,
+                                                      const int32_t* __restrict__ coors, const int32_t* __restrict__ num_voxels,
+                                                      int B, int V, int per, int coor_cols, float* __restrict__ out_voxels,
+                                                      int32_t* __restrict__ out_num, int32_t* __restrict__ out_coors,
+                                                      int64_t* __restrict__ out_total) {
+  __shared__ long long s_base;
+  const int b = blockIdx.y;
+  if (threadIdx.x < 32) {
+    long long acc = 0;
+    for (int g = threadIdx.x; g < b; g += 32) {
+      int nv = num_voxels[g];
+      acc += nv < 0 ? 0 : (nv > V ? V : nv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) s_base = acc;
+  }
+  __syncthreads();
+  int nv = num_voxels[b];
+  nv = nv < 0 ? 0 : (nv > V ? V : nv);
+  const long long base = s_base;
+  if (b == B - 1 && blockIdx.x == 0 && threadIdx.x == 0) *out_total = base + nv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec = (per & 3) == 0 && ((reinterpret_cast<uintptr_t>(voxels) | reinterpret_cast<uintptr_t>(out_voxels)) & 15) == 0;
+  for (int r = blockIdx.x * 8 + warp; r < nv; r += gridDim.x * 8) {
+    const long long src = (long long)b * V + r, dst = base + r;
+    if (vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(voxels + src * per);
+      float4* d4 = reinterpret_cast<float4*>(out_voxels + dst * per);
+      for (int i = lane; i < per / 4; i += 32) lv_st_stream_f4(d4 + i, lv_ld_stream_f4(s4 + i));
+    } else {
+      for (int i = lane; i < per; i += 32) out_voxels[dst * per + i] = voxels[src * per + i];
+    }
+    if (lane == 0) out_num[dst] = num_points[src];
+    if (lane < coor_cols) out_coors[dst * coor_cols + lane] = coors[src * coor_cols + lane];
+  }
+}
+
 // ================================================================= host side
 extern "C" int lv_voxel_grid_size(const lv_voxel_config* cfg, int32_t grid_xyz[3]) {
   LV_REQUIRE(cfg && grid_xyz, "lv_voxel_grid_size: null argument");
@@ -1006,5 +1049,26 @@ extern "C" int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const 
                                   cudaMemcpyDeviceToHost, st));
   }
   LV_CHECK_CUDA(cudaStreamSynchronize(st));
+  return LV_OK;
+}
+
+extern "C" int lv_unpad_batch(lv_handle* h, const float* d_voxels, const int32_t* d_num_points, const int32_t* d_coors,
+                              const int32_t* d_num_voxels, int32_t batch_size, int32_t max_voxels, int32_t max_points,
+                              int32_t num_features, int32_t coor_cols, float* d_out_voxels, int32_t* d_out_num_points,
+                              int32_t* d_out_coors, int64_t* d_out_total, lv_stream stream_) {
+  LV_REQUIRE(h != nullptr, "lv_unpad_batch: null handle");
+  LV_REQUIRE(batch_size >= 0 && max_voxels > 0 && max_points > 0 && num_features > 0 && coor_cols > 0 && coor_cols <= 32,
+             "lv_unpad_batch: bad sizes");
+  if (batch_size == 0) return LV_OK;
+  LV_REQUIRE(d_voxels && d_num_points && d_coors && d_num_voxels && d_out_voxels && d_out_num_points && d_out_coors &&
+                 d_out_total, "lv_unpad_batch: null pointer");
+  LV_CHECK_CUDA(cudaSetDevice(h->device));
+  int gx = (int)lv_div_up((int64_t)h->num_sms * 8, batch_size);
+  const int max_gx = (int)lv_div_up(max_voxels, 8);
+  if (gx > max_gx) gx = max_gx;
+  vx_unpad_kernel<<<dim3((unsigned)gx, (unsigned)batch_size), 256, 0, (cudaStream_t)stream_>>>(
+      d_voxels, d_num_points, d_coors, d_num_voxels, batch_size, max_voxels, max_points * num_features, coor_cols,
+      d_out_voxels, d_out_num_points, d_out_coors, d_out_total);
+  LV_LAUNCH_CHECK(h);
   return LV_OK;
 }

@@ -173,3 +173,32 @@ def points_to_voxel(points, voxel_size, coors_range, max_points=35, reverse_inde
     if not reverse_index:
         co = co.flip(-1) if _is_cuda_tensor(co) else co[:, ::-1].copy()
     return voxels[0][:k], co, num[0][:k]
+
+
+def unpad_multigpu_batch(voxels, num_points, coordinates, num_voxels):
+    """The un-padding at the top of VoxelNet.forward (voxelnet.py:346-358) on the device:
+    padded (B,V,T,C) / (B,V) / (B,V,4) CUDA tensors + num_voxels (B) -> concatenated
+    (sum,T,C) / (sum) / (sum,4).  One host read (the total), like the reference's
+    ``example["num_voxels"].cpu()``."""
+    import torch
+    lib = nat.load()
+    if not (voxels.is_cuda and voxels.dtype == torch.float32):
+        raise ValueError("voxels must be a float32 CUDA tensor")
+    voxels = voxels.contiguous()
+    B, V, T, C = voxels.shape
+    num = num_points.to(torch.int32).contiguous()
+    co = coordinates.to(torch.int32).contiguous()
+    nv = num_voxels.to(device=voxels.device, dtype=torch.int32).reshape(-1).contiguous()
+    cols = co.shape[-1]
+    dev = voxels.device
+    out_v = torch.empty((B * V, T, C), dtype=torch.float32, device=dev)
+    out_n = torch.empty((B * V,), dtype=torch.int32, device=dev)
+    out_c = torch.empty((B * V, cols), dtype=torch.int32, device=dev)
+    total = torch.zeros((1,), dtype=torch.int64, device=dev)
+    h = nat.get_handle(dev.index)
+    with torch.cuda.device(dev):
+        nat.check(lib.lv_unpad_batch(h.ptr, voxels.data_ptr(), num.data_ptr(), co.data_ptr(), nv.data_ptr(), B, V, T, C,
+                                     cols, out_v.data_ptr(), out_n.data_ptr(), out_c.data_ptr(), total.data_ptr(),
+                                     nat.current_stream_ptr(dev)))
+    n = int(total.item())
+    return out_v[:n], out_n[:n], out_c[:n]

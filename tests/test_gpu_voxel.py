@@ -219,3 +219,24 @@ def test_tma_staged_chunks_equal_plain_loads(vg, vo, cloud11, C):
             v, c, n, k = orc.generate(fr, padded=True)
             assert vnum[f] == k and np.array_equal(coords[f], c) and np.array_equal(num[f], n), (off, f)
             assert np.array_equal(voxels[f].view(np.uint32), v.view(np.uint32)), (off, f)
+
+
+def test_unpad_multigpu_batch_equals_voxelnet_forward(vg, vo):
+    """generate_multi_gpu padding (preprocess.py:311-317) -> merge_second_batch_multigpu
+    (:60-88) -> the un-padding of VoxelNet.forward (voxelnet.py:346-358)."""
+    import torch
+    frames = [synth.c5_frame(40 + f)[: 9000 + 1500 * f] for f in range(4)] + [np.zeros((0, 4), np.float32)]
+    V, T = 6000, 7
+    gen = vg.VoxelGeneratorV2(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, T, max_voxels=V)
+    res = [gen.generate_multi_gpu(fr, V) for fr in frames]
+    voxels = torch.from_numpy(np.stack([r["voxels"] for r in res])).cuda()
+    num = torch.from_numpy(np.stack([r["num_points_per_voxel"] for r in res])).cuda()
+    coors = torch.from_numpy(np.stack([np.pad(r["coordinates"], ((0, 0), (1, 0)), mode="constant", constant_values=i)
+                                       for i, r in enumerate(res)])).cuda()
+    nv = torch.tensor([int(r["voxel_num"]) for r in res])
+    v2, n2, c2 = vg.unpad_multigpu_batch(voxels, num, coors, nv)
+    ref_v = torch.cat([voxels[i, :k] for i, k in enumerate(nv.tolist())], dim=0)
+    ref_n = torch.cat([num[i, :k] for i, k in enumerate(nv.tolist())], dim=0)
+    ref_c = torch.cat([coors[i, :k] for i, k in enumerate(nv.tolist())], dim=0)
+    assert v2.shape == ref_v.shape and bool((v2.view(torch.int32) == ref_v.view(torch.int32)).all())
+    assert bool((n2 == ref_n).all()) and bool((c2 == ref_c).all())
