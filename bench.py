@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=128)
     ap.add_argument("--pool-frames", type=int, default=256)
-    ap.add_argument("--cpu-frames", type=int, default=64)
+    ap.add_argument("--cpu-frames", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="voxelize and decorate as separate stages")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
@@ -347,12 +347,24 @@ def main():
             stage_info[st] = {"ms_per_step": round(ms, 4), "algorithmic_MB_per_step": round(alg[st] / 1e6, 2),
                               "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
         dom = max(stages, key=lambda s: stage_ms[s])
-        kernel_names = {"bev": "bev_hist_kernel+bev_finalize_flat4_kernel", "voxelize": "vx_* (13 kernels)",
-                        "decorate": "pillar_decorate_fast_kernel", "scatter": "pillar_canvas_kernel",
-                        "pillarize": "vx_* (12 kernels) + vx_gather_decorate_kernel"}
+        kernel_names = {"bev": "bev_hist_kernel + bev_finalize_flat4_kernel",
+                        "voxelize": "vx_cells/assign/keys/scan_hist/scatter + vx_bins_kernel<voxels>",
+                        "decorate": "pillar_decorate_fast_kernel",
+                        "scatter": "pillar_canvas_kernel (+ pillar_index_kernel, 1.5% of the stage)",
+                        "pillarize": "vx_cells/assign/keys/scan_hist/scatter + vx_bins_kernel<decorate>"}
+        # DRAM traffic of the dominant kernel per launch from the committed ncu --set full capture
+        # (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum at this workload)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            if tj.get("frames_per_step") == F and dom in tj.get("stages", {}):
+                traffic = tj["stages"][dom]["dram_bytes_per_launch"]
         roof = {"bound": "hbm", "kernel": kernel_names[dom], "stage": dom,
                 "achieved": stage_info[dom]["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": round(stage_info[dom]["GBps"] / peak, 4), "traffic": None,
+                "frac": round(stage_info[dom]["GBps"] / peak, 4), "traffic": traffic,
+                "algorithmic_bytes_per_launch": int(alg[dom]),
                 "whole_step_frac": round(sum(alg[st] for st in stages) / (ms_total / args.steps * 1e-3) / 1e9 / peak, 4)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
