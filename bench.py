@@ -127,6 +127,50 @@ def make_pool_frames(n_frames, device, seed):
     return out.reshape(n_frames * n, 4), n
 
 
+def time_other_configs(dev, reps=10):
+    """BASELINE.json configs[1..3] as single-cloud latencies (CUDA events, median of `reps`, inputs
+    resident on the device; the headline workload is configs[4])."""
+    import numpy as np
+    import torch
+    from lyft3d_b200 import bev, synth, voxel_generator as vg
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return float(np.median(ms))
+
+    cloud = torch.from_numpy(synth.multisweep_cloud(20)).to(dev)       # 1,062,920 points, 10+ sweeps
+    n = int(cloud.shape[0])
+    offs = np.array([0, n], dtype=np.int64)
+    out = {}
+    for name, vs, rg, T, V in (("C2 SECOND 0.05 m voxels, T=5, V=60000", synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, 60000),
+                               ("C3 pillars 0.25 m, T=60, V=30000", synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)):
+        ms = timed(lambda: vg.voxelize_frames(cloud, offs, vs, rg, T, V, zero_tail=False))
+        out[name] = {"points": n, "ms": round(ms, 4), "points_per_s": round(n / (ms * 1e-3))}
+    # C4: 1024^2 x 3 BEV of the same cloud, 20 sweeps each with its own sensor->car 4x4, u8 + CHW/map
+    per = n // 20
+    seg_offs = np.arange(21, dtype=np.int64) * per
+    seg_tm = np.stack([synth.sweep_transform(s) for s in range(20)])
+    maps = torch.from_numpy(synth.map_raster(seed=4000)[None]).to(dev)
+    res = {"u8": torch.empty((1,) + synth.BEV1024_SHAPE, dtype=torch.uint8, device=dev),
+           "chw": torch.empty((1, 6, 1024, 1024), dtype=torch.float32, device=dev)}
+    ms = timed(lambda: bev.rasterize_frames(cloud, seg_offs, synth.BEV1024_SHAPE, synth.BEV1024_VOXEL_SIZE,
+                                            synth.BEV_Z_OFFSET, seg_frame=np.zeros(20, np.int32), seg_tm=seg_tm,
+                                            n_frames=1, want=("u8", "chw"), map_u8=maps, out=res))
+    out["C4 BEV 1024x1024x3, 20 sweeps with 4x4, u8 + (6,1024,1024) CHW with map"] = {
+        "points": n, "ms": round(ms, 4), "points_per_s": round(n / (ms * 1e-3))}
+    return out
+
+
 def cpu_baseline(n_frames, workers):
     from oracle import cpu_path
     cfg = workload_cfg()
@@ -178,6 +222,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="voxelize and decorate as separate stages")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the single-cloud timings of configs[1..3]")
+    ap.add_argument("--serial", action="store_true", help="headline from the one-stream loop (no stream pipelining)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
@@ -251,7 +297,27 @@ def main():
             rows_seen.append(rows)
         return evs, rows_seen
 
+    # ---- pass 1: stages back to back on one stream, CUDA events around every stage ---------
+    # (the per-stage times behind `stages` and `roofline`)
     run_steps(args.warmup, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    evs, rows_seen = run_steps(args.steps, True)
+    t_end.record()
+    torch.cuda.synchronize()
+    serial_ms_total = t_start.elapsed_time(t_end)
+
+    # ---- pass 2 (the headline): the same steps through PipelinedEngine - BEV and the voxelizer of
+    # step i+1 run on high-priority streams next to the canvas stream of step i, no host sync
+    from lyft3d_b200.engine import PipelinedEngine
+    pipe_eng = PipelinedEngine(eng) if fused and not args.serial else None
+    if pipe_eng is not None:
+        for s in range(args.warmup):
+            pipe_eng.submit(batch(s))
+        pipe_eng.drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -262,7 +328,12 @@ def main():
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_start.record()
-    evs, rows_seen = run_steps(args.steps, True)
+    if pipe_eng is not None:
+        for s in range(args.steps):
+            pipe_eng.submit(batch(s))
+        pipe_eng.drain()
+    else:
+        run_steps(args.steps, False)
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -315,10 +386,10 @@ def main():
         pipe.run(host_batches, args.steps)
         e2e_sec = time.perf_counter() - t0
 
-    t = torch.tensor([ms_total, e2e_sec], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_sec, serial_ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_sec = float(t[0]), float(t[1])
+    ms_total, e2e_sec, serial_ms_total = float(t[0]), float(t[1]), float(t[2])
     pts_per_step_all = F * n * world
     value = pts_per_step_all * args.steps / (ms_total * 1e-3)
     e2e_value = pts_per_step_all * args.steps / e2e_sec
@@ -370,8 +441,12 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 points, f64 BEV affine, u32 counts",
                 "data": "synthetic",
-                "config": config_json(F, world, {"mean_pillars_per_frame": round(mean_rows / F, 1), "unfused": not fused}),
+                "config": config_json(F, world, {"mean_pillars_per_frame": round(mean_rows / F, 1), "unfused": not fused,
+                                                 "execution": "stages of neighbouring steps overlap on 3 streams "
+                                                              "(PipelinedEngine), no host sync" if pipe_eng is not None
+                                                 else "one stream, stages back to back"}),
                 "roofline": roof, "stages": stage_info,
+                "one_stream_ms_per_step": round(serial_ms_total / args.steps, 4),
                 "pillar_path_with_fused_pfn": None if pfn_ms is None else {
                     "ms_per_step": round(pfn_ms, 4),
                     "note": "points -> voxelize+decorate+PFNLayer(eval) in one pipeline -> scatter; the unfused "
@@ -382,6 +457,8 @@ def main():
                         "note": "HostPipeline: pinned host points -> device -> both paths -> BEV u8 + voxel_num "
                                 "back in pinned host memory every step (copies overlap the next step's kernels); "
                                 "the canvas stays on the device (its consumer is the RPN, voxelnet.py:336)"}}
+        if world == 1 and not args.no_other_configs:
+            line["other_configs"] = time_other_configs(dev)
         if world == 1 and not args.no_cpu_baseline:
             v, pts, sec = cpu_baseline(args.cpu_frames, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",

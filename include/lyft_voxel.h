@@ -298,6 +298,14 @@ int lv_pillar_scatter(lv_handle* h, const float* d_feats, const int32_t* d_coord
                       int64_t n_pillars, int32_t channels, int32_t batch_size, int32_t ny,
                       int32_t nx, float* d_canvas, lv_stream stream);
 
+/* Same, with the pillar count read on the device (*d_n_pillars, e.g. d_voxel_offsets[n_frames] of
+ * lv_voxelize_concat; rows at and beyond min(*d_n_pillars, max_pillars) are ignored): the host
+ * never waits for the voxelizer, so consecutive frames pipeline across streams. */
+int lv_pillar_scatter_dev(lv_handle* h, const float* d_feats, const int32_t* d_coords,
+                          const int64_t* d_n_pillars, int64_t max_pillars, int32_t channels,
+                          int32_t batch_size, int32_t ny, int32_t nx, float* d_canvas,
+                          lv_stream stream);
+
 /* SimpleVoxel.forward (second/second/pytorch/models/voxel_encoder.py:219-225):
  * out[p, c] = sum_t voxels[p, t, c] / num[p] for c < num_features_out. */
 int lv_voxel_mean(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,

@@ -178,9 +178,14 @@ static void pillar_pfn_launch(int units, unsigned blocks, size_t smem, cudaStrea
 }
 
 // ---------------------------------------------------------------- scatter
-__global__ void __launch_bounds__(256) pillar_index_kernel(const int32_t* __restrict__ coords, int64_t P, int B, int ny,
-                                                         int nx, int32_t* __restrict__ map) {
+__global__ void __launch_bounds__(256) pillar_index_kernel(const int32_t* __restrict__ coords, int64_t P,
+                                                         const int64_t* __restrict__ d_P, int B, int ny, int nx,
+                                                         int32_t* __restrict__ map) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_P) {   // the pillar count lives on the device (no host round trip): P is only the bound
+    const int64_t n = __ldg(d_P);
+    if (n < P) P = n;
+  }
   if (p >= P) return;
   const int4 c = __ldg(reinterpret_cast<const int4*>(coords) + p);  // b, z, y, x
   if (c.x < 0 || c.x >= B || c.z < 0 || c.z >= ny || c.w < 0 || c.w >= nx) return;
@@ -350,9 +355,9 @@ extern "C" int lv_pillar_pfn(lv_handle* h, const float* d_voxels, const int32_t*
   return LV_OK;
 }
 
-extern "C" int lv_pillar_scatter(lv_handle* h, const float* d_feats, const int32_t* d_coords, int64_t n_pillars,
-                                 int32_t channels, int32_t batch_size, int32_t ny, int32_t nx, float* d_canvas,
-                                 lv_stream stream_) {
+static int pillar_scatter_run(lv_handle* h, const float* d_feats, const int32_t* d_coords, int64_t n_pillars,
+                              const int64_t* d_n_pillars, int32_t channels, int32_t batch_size, int32_t ny, int32_t nx,
+                              float* d_canvas, lv_stream stream_) {
   LV_REQUIRE(h != nullptr, "lv_pillar_scatter: null handle");
   LV_REQUIRE(n_pillars >= 0 && channels > 0 && batch_size >= 0 && ny > 0 && nx > 0, "lv_pillar_scatter: bad sizes");
   if (batch_size == 0) return LV_OK;
@@ -365,8 +370,8 @@ extern "C" int lv_pillar_scatter(lv_handle* h, const float* d_feats, const int32
   const int64_t ncell = (int64_t)ny * nx;
   LV_CHECK(h->pil_map.ensure((size_t)batch_size * ncell * sizeof(int32_t), stream, 0xff));
   if (n_pillars > 0) {
-    pillar_index_kernel<<<(unsigned)lv_div_up(n_pillars, 256), 256, 0, stream>>>(d_coords, n_pillars, batch_size, ny, nx,
-                                                                               h->pil_map.as<int32_t>());
+    pillar_index_kernel<<<(unsigned)lv_div_up(n_pillars, 256), 256, 0, stream>>>(d_coords, n_pillars, d_n_pillars,
+                                                                               batch_size, ny, nx, h->pil_map.as<int32_t>());
     LV_LAUNCH_CHECK(h);
   }
   const int tiles = (int)lv_div_up(ncell, SC_TILE);
@@ -388,6 +393,19 @@ extern "C" int lv_pillar_scatter(lv_handle* h, const float* d_feats, const int32
   }
   LV_LAUNCH_CHECK(h);
   return LV_OK;
+}
+
+extern "C" int lv_pillar_scatter(lv_handle* h, const float* d_feats, const int32_t* d_coords, int64_t n_pillars,
+                                 int32_t channels, int32_t batch_size, int32_t ny, int32_t nx, float* d_canvas,
+                                 lv_stream stream) {
+  return pillar_scatter_run(h, d_feats, d_coords, n_pillars, nullptr, channels, batch_size, ny, nx, d_canvas, stream);
+}
+
+extern "C" int lv_pillar_scatter_dev(lv_handle* h, const float* d_feats, const int32_t* d_coords,
+                                     const int64_t* d_n_pillars, int64_t max_pillars, int32_t channels,
+                                     int32_t batch_size, int32_t ny, int32_t nx, float* d_canvas, lv_stream stream) {
+  LV_REQUIRE(d_n_pillars != nullptr, "lv_pillar_scatter_dev: null pillar count");
+  return pillar_scatter_run(h, d_feats, d_coords, max_pillars, d_n_pillars, channels, batch_size, ny, nx, d_canvas, stream);
 }
 
 extern "C" int lv_voxel_mean(lv_handle* h, const float* d_voxels, const int32_t* d_num_points, int64_t n_voxels,

@@ -151,6 +151,85 @@ class FrameBatchEngine:
         return rows
 
 
+class PipelinedEngine:
+    """Stream-pipelined driver of a FrameBatchEngine: no host synchronisation anywhere.
+
+    The hot path mixes latency/atomic-bound kernels (BEV histogram, the voxelizer's order
+    reconstruction) with pure HBM streams (the decorated rows, the 41 MB/frame canvas).  Run back to
+    back on one stream the first kind leaves the memory system idle; here they run on
+    high-priority streams NEXT TO the streaming kernels of the neighbouring step:
+
+        s_bev (high)  BEV(i)
+        s_vox (high)  voxelize+decorate(i)            -> buffer set i % 2
+        s_sc  (low)   scatter(i) waits for s_vox(i)   <- buffer set i % 2, pillar count read on the
+                                                         device (lv_pillar_scatter_dev)
+
+    so scatter(i) overlaps BEV(i+1) and the voxelizer of step i+1.  Results are identical to
+    FrameBatchEngine.step (tests/test_gpu_engine.py); set 0 aliases the engine's own buffers.
+    """
+
+    def __init__(self, engine, bev_priority=-1, vox_priority=-1, scatter_priority=0):
+        import os as _os
+        e = self.eng = engine
+        d = e.dev
+        bev_priority = int(_os.environ.get("LV_PIPE_BEV_PRIO", bev_priority))
+        vox_priority = int(_os.environ.get("LV_PIPE_VOX_PRIO", vox_priority))
+        scatter_priority = int(_os.environ.get("LV_PIPE_SC_PRIO", scatter_priority))
+        self.s_bev = torch.cuda.Stream(d, priority=bev_priority)
+        self.s_vox = torch.cuda.Stream(d, priority=vox_priority)
+        self.s_sc = torch.cuda.Stream(d, priority=scatter_priority)
+        self.sets = [dict(coords=e.coords, num_points=e.num_points, voxel_num=e.voxel_num,
+                          voxel_offsets=e.voxel_offsets, decorated=e.decorated)]
+        self.sets.append(dict(coords=torch.empty_like(e.coords), num_points=torch.empty_like(e.num_points),
+                              voxel_num=torch.empty_like(e.voxel_num), voxel_offsets=torch.empty_like(e.voxel_offsets),
+                              decorated=torch.empty_like(e.decorated)))
+        self.ev_vox = [torch.cuda.Event() for _ in range(2)]   # voxelizer of the set finished
+        self.ev_sc = [torch.cuda.Event() for _ in range(2)]    # scatter has consumed the set
+        self.ev_bev = torch.cuda.Event()
+        self.i = 0
+
+    def submit(self, points, features=None):
+        """Enqueues one step over `points` (valid on the caller's current stream) and returns
+        the buffer set its pillar outputs land in.  Nothing is synchronised."""
+        e = self.eng
+        k = self.i & 1
+        st = self.sets[k]
+        cur = torch.cuda.current_stream(e.dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self.s_bev):
+            self.s_bev.wait_event(ready)
+            e.bev(points)
+            self.ev_bev.record(self.s_bev)
+        with torch.cuda.stream(self.s_vox):
+            self.s_vox.wait_event(ready)
+            if self.i >= 2:
+                self.s_vox.wait_event(self.ev_sc[k])     # scatter(i-2) has read this set
+            nat.check(e.lib.lv_pillarize_concat(
+                e.h.ptr, ctypes.byref(e.cfg), points.data_ptr(), e.F, e.offsets.ctypes.data, e.cap, e.vx, e.vy,
+                e.x_off, e.y_off, 0, 0, st["decorated"].data_ptr(), st["coords"].data_ptr(),
+                st["num_points"].data_ptr(), st["voxel_num"].data_ptr(), st["voxel_offsets"].data_ptr(),
+                self.s_vox.cuda_stream))
+            self.ev_vox[k].record(self.s_vox)
+        with torch.cuda.stream(self.s_sc):
+            self.s_sc.wait_event(self.ev_vox[k])
+            feats = e.features if features is None else features
+            nat.check(e.lib.lv_pillar_scatter_dev(
+                e.h.ptr, feats.data_ptr(), st["coords"].data_ptr(), st["voxel_offsets"][e.F:].data_ptr(), e.cap,
+                e.channels, e.F, e.ny, e.nx, e.canvas.data_ptr(), self.s_sc.cuda_stream))
+            self.ev_sc[k].record(self.s_sc)
+        self.i += 1
+        return st
+
+    def drain(self):
+        """Makes the caller's current stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream(self.eng.dev)
+        for s in (self.s_bev, self.s_vox, self.s_sc):
+            ev = torch.cuda.Event()
+            ev.record(s)
+            cur.wait_event(ev)
+
+
 class HostPipeline:
     """End-to-end driver with HOST buffers on both sides of a FrameBatchEngine.
 

@@ -98,3 +98,41 @@ def test_shard_frames():
     got = sorted(sum((shard_frames(8192, r, 8) for r in range(8)), []))
     assert got == list(range(8192))
     assert shard_frames(10, 1, 4) == [1, 5, 9]
+
+
+def test_pipelined_engine_equals_serial_steps():
+    """Stream-pipelined steps (no host sync, device-side pillar count, two buffer sets) leave
+    exactly the bits of FrameBatchEngine.step."""
+    import torch
+    from lyft3d_b200.engine import FrameBatchEngine, PipelinedEngine
+    F = 5
+    batches = []
+    for b in range(3):
+        frames = [synth.c5_frame(300 + 10 * b + f) for f in range(F)]
+        batches.append(torch.from_numpy(np.concatenate(frames)).cuda())
+    n = batches[0].shape[0] // F
+    eng = FrameBatchEngine(0, F, n)
+    torch.manual_seed(7)
+    eng.features.copy_(torch.randn_like(eng.features))
+    want = []
+    for pts in batches:
+        rows = eng.step(pts)
+        want.append((rows, eng.bev_u8.clone(), eng.canvas.clone(), eng.coords[:rows].clone(),
+                     eng.decorated[:rows].clone()))
+    pipe = PipelinedEngine(eng)
+    for b, pts in enumerate(batches):
+        st = pipe.submit(pts)
+        pipe.drain()
+        torch.cuda.synchronize()
+        rows, u8, canvas, coords, dec = want[b]
+        assert int(st["voxel_offsets"][F]) == rows
+        assert bool((eng.bev_u8 == u8).all()) and bool((eng.canvas == canvas).all())
+        assert bool((st["coords"][:rows] == coords).all()) and bool((st["decorated"][:rows] == dec).all())
+    # back to back without draining in between: the last step's outputs are still right
+    for pts in batches:
+        st = pipe.submit(pts)
+    pipe.drain()
+    torch.cuda.synchronize()
+    rows, u8, canvas, coords, dec = want[-1]
+    assert bool((eng.canvas == canvas).all()) and bool((eng.bev_u8 == u8).all())
+    assert bool((st["coords"][:rows] == coords).all())
