@@ -192,68 +192,94 @@ __global__ void __launch_bounds__(256) pillar_index_kernel(const int32_t* __rest
   map[(int64_t)c.x * ny * nx + (int64_t)c.z * nx + c.w] = (int32_t)p;
 }
 
-#define SC_TILE 128
-#define SC_LD (SC_TILE + 4)   // 16-byte aligned rows: the read-out is one conflict-free LDS.128 per lane
+#define SC_THREADS 256
+#define SC_WARPS (SC_THREADS / 32)
+#define SC_TILE 128   // cells per CTA: every lane owns 4 consecutive cells (one float4 per channel row)
 
-// One CTA = one tile of 128 consecutive cells x all C channels of one sample.  Occupied
-// cells drop their feature row into the transposed shared-memory tile; the read-out masks
-// with the cell->pillar index, so the tile is never zero-filled.
+// One CTA = 128 consecutive cells x all C channels of one sample.  No shared memory and at most
+// 32 registers, so eight CTAs (64 warps) fit on an SM: the kernel is a store stream whose rate
+// follows the number of CTAs in flight (measured: 1.55 / 1.32 / 1.16 / 1.04 ms at 3 / 4 / 5 / 6
+// CTAs per SM for the shared-memory-tile version of this kernel).
+//   - every lane reads the cell->pillar indices of ITS four cells (a "quad") into registers; the
+//     eight warps read the same 512 bytes, so all of them take the same branch below;
+//   - no occupied cell in the tile: one 128-bit zero store per lane and channel row;
+//   - otherwise every lane gathers four features per row - an empty cell reads pillar 0's row,
+//     which stays in L1, and discards it - so the warp never diverges inside the row loop.
+// Warp 0 leaves the map empty for the next call once every warp has read it (the barrier sits
+// in front of the stores and waits for nothing but the index loads).
 template <bool VEC>
-__global__ void __launch_bounds__(256) pillar_canvas_kernel(const float* __restrict__ feats, int32_t* __restrict__ map,
-                                                          int C, int64_t ncell, int tiles_per_sample,
-                                                          float* __restrict__ canvas) {
-  extern __shared__ __align__(16) float tile[];  // [C][SC_LD]
-  __shared__ __align__(16) int32_t idx[SC_TILE];
+__global__ void __launch_bounds__(SC_THREADS, 8) pillar_canvas_kernel(const float* __restrict__ feats, int32_t* __restrict__ map,
+                                                                    int C, int64_t ncell, int tiles_per_sample,
+                                                                    float* __restrict__ canvas) {
   const int b = blockIdx.x / tiles_per_sample;
   const int t = blockIdx.x - b * tiles_per_sample;
   const int64_t cell0 = (int64_t)t * SC_TILE;
   const int n_here = (int)((ncell - cell0) < SC_TILE ? (ncell - cell0) : SC_TILE);
   int32_t* m = map + (int64_t)b * ncell + cell0;
-  int mine = -1;
-  if (threadIdx.x < SC_TILE) {
-    if ((int)threadIdx.x < n_here) {
-      mine = m[threadIdx.x];
-      if (mine >= 0) m[threadIdx.x] = -1;    // leave the map empty for the next call
-    }
-    idx[threadIdx.x] = mine;
-  }
-  const int any = __syncthreads_or(mine >= 0);
-  float* dst = canvas + (int64_t)b * C * ncell + cell0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = lane * 4;
   const bool full = VEC && n_here == SC_TILE;
+  int4 occ = make_int4(-1, -1, -1, -1);
+  if (full) {
+    occ = *reinterpret_cast<const int4*>(m + j0);
+  } else {
+    if (j0 < n_here) occ.x = m[j0];
+    if (j0 + 1 < n_here) occ.y = m[j0 + 1];
+    if (j0 + 2 < n_here) occ.z = m[j0 + 2];
+    if (j0 + 3 < n_here) occ.w = m[j0 + 3];
+  }
+  const bool mine = (occ.x & occ.y & occ.z & occ.w) >= 0;   // any of the four >= 0 (sign bit clear)
+  const bool any = __syncthreads_or(mine);
+  if (any && warp == 0 && mine) {
+    if (occ.x >= 0) m[j0] = -1;
+    if (occ.y >= 0) m[j0 + 1] = -1;
+    if (occ.z >= 0) m[j0 + 2] = -1;
+    if (occ.w >= 0) m[j0 + 3] = -1;
+  }
+  float* row = canvas + ((int64_t)b * C + warp) * ncell + cell0 + j0;
+  const int64_t row_step = (int64_t)SC_WARPS * ncell;
   if (!any) {
-    // empty tile: pure streaming zero fill
-    for (int c = warp; c < C; c += 8) {
-      float* row = dst + (int64_t)c * ncell;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = warp; c < C; c += SC_WARPS, row += row_step) {
       if (full) {
-        lv_st_stream_f4(reinterpret_cast<float4*>(row) + lane, make_float4(0.f, 0.f, 0.f, 0.f));
+        lv_st_stream_f4(reinterpret_cast<float4*>(row), z4);
       } else {
-        for (int j = lane; j < n_here; j += 32) row[j] = 0.f;
+        if (j0 < n_here) row[0] = 0.f;
+        if (j0 + 1 < n_here) row[1] = 0.f;
+        if (j0 + 2 < n_here) row[2] = 0.f;
+        if (j0 + 3 < n_here) row[3] = 0.f;
       }
     }
     return;
   }
-  for (int j = warp; j < n_here; j += 8) {
-    const int pi = idx[j];
-    if (pi < 0) continue;
-    const float* f = feats + (int64_t)pi * C;
-    for (int c = lane; c < C; c += 32) tile[c * SC_LD + j] = __ldg(f + c);
-  }
-  __syncthreads();
-  if (full) {
-    const int4 occ = reinterpret_cast<const int4*>(idx)[lane];
-    for (int c = warp; c < C; c += 8) {
-      float4 v = reinterpret_cast<const float4*>(tile + c * SC_LD)[lane];
-      v.x = occ.x >= 0 ? v.x : 0.f;
-      v.y = occ.y >= 0 ? v.y : 0.f;
-      v.z = occ.z >= 0 ? v.z : 0.f;
-      v.w = occ.w >= 0 ? v.w : 0.f;
-      lv_st_stream_f4(reinterpret_cast<float4*>(dst + (int64_t)c * ncell) + lane, v);
-    }
-  } else {
-    for (int c = warp; c < C; c += 8) {
-      float* row = dst + (int64_t)c * ncell;
-      for (int j = lane; j < n_here; j += 32) row[j] = idx[j] >= 0 ? tile[c * SC_LD + j] : 0.f;
+  // feature offsets (pillar * C fits 32 bits: checked by the host); empty cells point at pillar 0
+  const unsigned ox = occ.x < 0 ? 0u : (unsigned)occ.x * (unsigned)C, oy = occ.y < 0 ? 0u : (unsigned)occ.y * (unsigned)C,
+                 oz = occ.z < 0 ? 0u : (unsigned)occ.z * (unsigned)C, ow = occ.w < 0 ? 0u : (unsigned)occ.w * (unsigned)C;
+  // software pipeline: the gathers of the next row are in flight while this row is stored
+  float4 nx;
+  nx.x = __ldg(feats + ox + warp);
+  nx.y = __ldg(feats + oy + warp);
+  nx.z = __ldg(feats + oz + warp);
+  nx.w = __ldg(feats + ow + warp);
+#pragma unroll 1
+  for (int c = warp; c < C; c += SC_WARPS, row += row_step) {
+    float4 v = nx;
+    const int cn = c + SC_WARPS < C ? c + SC_WARPS : c;
+    nx.x = __ldg(feats + ox + cn);
+    nx.y = __ldg(feats + oy + cn);
+    nx.z = __ldg(feats + oz + cn);
+    nx.w = __ldg(feats + ow + cn);
+    v.x = occ.x >= 0 ? v.x : 0.f;
+    v.y = occ.y >= 0 ? v.y : 0.f;
+    v.z = occ.z >= 0 ? v.z : 0.f;
+    v.w = occ.w >= 0 ? v.w : 0.f;
+    if (full) {
+      lv_st_stream_f4(reinterpret_cast<float4*>(row), v);
+    } else {
+      if (j0 < n_here) row[0] = v.x;
+      if (j0 + 1 < n_here) row[1] = v.y;
+      if (j0 + 2 < n_here) row[2] = v.z;
+      if (j0 + 3 < n_here) row[3] = v.w;
     }
   }
 }
@@ -375,22 +401,17 @@ static int pillar_scatter_run(lv_handle* h, const float* d_feats, const int32_t*
     LV_LAUNCH_CHECK(h);
   }
   const int tiles = (int)lv_div_up(ncell, SC_TILE);
-  const size_t smem = (size_t)channels * SC_LD * sizeof(float);
-  LV_REQUIRE(smem <= 200 * 1024, "lv_pillar_scatter: too many channels (%d)", channels);
+  LV_REQUIRE(n_pillars * (int64_t)channels < (1ll << 32), "lv_pillar_scatter: %lld pillars x %d channels exceed 2^32 features",
+             (long long)n_pillars, channels);
   const bool vec = (ncell % 4 == 0) && (reinterpret_cast<uintptr_t>(d_canvas) & 15) == 0;
   const int64_t grid = (int64_t)tiles * batch_size;
   LV_REQUIRE(grid < (1ll << 31), "lv_pillar_scatter: canvas too large");
-  if (vec) {
-    if (smem > 48 * 1024)
-      LV_CHECK_CUDA(cudaFuncSetAttribute(pillar_canvas_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pillar_canvas_kernel<true><<<(unsigned)grid, 256, smem, stream>>>(d_feats, h->pil_map.as<int32_t>(), channels, ncell,
-                                                                    tiles, d_canvas);
-  } else {
-    if (smem > 48 * 1024)
-      LV_CHECK_CUDA(cudaFuncSetAttribute(pillar_canvas_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pillar_canvas_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(d_feats, h->pil_map.as<int32_t>(), channels, ncell,
-                                                                     tiles, d_canvas);
-  }
+  if (vec)
+    pillar_canvas_kernel<true><<<(unsigned)grid, SC_THREADS, 0, stream>>>(d_feats, h->pil_map.as<int32_t>(), channels, ncell,
+                                                                        tiles, d_canvas);
+  else
+    pillar_canvas_kernel<false><<<(unsigned)grid, SC_THREADS, 0, stream>>>(d_feats, h->pil_map.as<int32_t>(), channels, ncell,
+                                                                         tiles, d_canvas);
   LV_LAUNCH_CHECK(h);
   return LV_OK;
 }
