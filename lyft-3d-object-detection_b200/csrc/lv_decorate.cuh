@@ -118,6 +118,51 @@ __device__ __forceinline__ void lv_decorate_warp(const float4 a, const float4 b,
   __syncwarp();
 }
 
+// Two small pillars (<= 16 points each) decorated by ONE warp at once: lanes 0-15 own pillar A,
+// lanes 16-31 pillar B, lane (sub) holds slot `sub` of its pillar in `a` (zeros beyond num).  The
+// sums run over the 16 lanes of a half (xor 8,4,2,1 never crosses bit 4) - the same additions, in
+// the same order, as the 32-lane tree of lv_decorate_stage sees for a pillar of <= 16 points, so
+// the result is bit-identical.  `st` is the half's own stage, `dst` the half's own output row;
+// the caller has already issued lv_decorate_zero_tail for both rows.  Needs T > 16 (padding slots
+// exist, which is what makes the z range of the RadiusHeight variant include 0).
+__device__ __forceinline__ void lv_decorate_half(const float4 a, int num, int coor_y, int coor_x, const DecoCfg& d,
+                                                 float* st, float* __restrict__ dst, int lane) {
+  const int sub = lane & 15;
+  float sx = a.x, sy = a.y, sz = a.z;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    sz += __shfl_xor_sync(0xffffffffu, sz, o);
+  }
+  const float fn = (float)num;
+  const float mx = __fdiv_rn(sx, fn), my = __fdiv_rn(sy, fn), mz = __fdiv_rn(sz, fn);
+  float height = 0.f;
+  if (d.variant == LV_PILLAR_RADIUS_HEIGHT) {  // :387-389: the padded slots contribute z = 0
+    float zmax = fmaxf(a.z, 0.f), zmin = fminf(a.z, 0.f);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+      zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+    }
+    height = zmax - zmin;
+  }
+  const float cx = __fadd_rn(__fmul_rn((float)coor_x, d.vx), d.x_off);
+  const float cy = __fadd_rn(__fmul_rn((float)coor_y, d.vy), d.y_off);
+  if (sub < num) lv_decorate_slot(a, mx, my, mz, cx, cy, height, d, st + sub * d.C_out);
+  const int nd = num * d.C_out;
+  if (sub < (((nd + 3) >> 2) << 2) - nd) st[nd + sub] = 0.f;  // pad the last quad of the data part
+  __syncwarp();
+  if (lv_row_vec4(d, dst)) {
+    const float4* s4 = reinterpret_cast<const float4*>(st);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = sub; i < ((nd + 3) >> 2); i += 16) lv_st_stream_f4(d4 + i, s4[i]);
+  } else {
+    for (int i = sub; i < nd; i += 16) dst[i] = st[i];
+  }
+  __syncwarp();
+}
+
 // ---- PFNLayer (second/second/pytorch/models/pointpillars.py:51-65), inference form, fused
 // behind the decoration: y = W f (Linear 9 -> units, no bias), z = relu(y * scale + shift)
 // (BatchNorm1d in eval mode folded to scale/shift on the host), out = max over the T slots.
