@@ -1,0 +1,132 @@
+"""GPU: no entry point writes outside the buffers it was given.  Every output is carved out of a
+larger allocation whose head and tail are filled with a sentinel; the sentinels must survive.
+(compute-sanitizer is closed on this pool, so the bounds are checked this way.)"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from lyft3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GUARD = 4096          # elements on each side
+SENT_F = 12345.678
+SENT_I = -123456789
+
+
+class Guarded:
+    def __init__(self, shape, dtype, device):
+        import torch
+        n = int(np.prod(shape)) if len(shape) else 1
+        self.sent = SENT_F if dtype.is_floating_point else (77 if dtype == torch.uint8 else SENT_I)
+        self.full = torch.full((n + 2 * GUARD,), self.sent, dtype=dtype, device=device)
+        self.t = self.full[GUARD:GUARD + n].view(shape) if n else self.full[GUARD:GUARD]
+        self.n = n
+
+    def intact(self):
+        return bool((self.full[:GUARD] == self.sent).all()) and bool((self.full[GUARD + self.n:] == self.sent).all())
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    assert torch.cuda.is_available()
+    from lyft3d_b200 import _native as nat
+    from lyft3d_b200.voxel_generator import _make_config
+    return torch, nat, nat.load(), nat.get_handle(0), _make_config
+
+
+def test_pillarize_at_the_capacity_boundary_and_scatter(env):
+    torch, nat, lib, h, make_cfg = env
+    dev = torch.device("cuda", 0)
+    F = 3
+    frames = [synth.c5_frame(500 + f)[:30000] for f in range(F)]
+    pts = torch.from_numpy(np.concatenate(frames)).to(dev)
+    offs = np.arange(F + 1, dtype=np.int64) * 30000
+    T, V = 60, 30000
+    cfg = make_cfg(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, T, V, 4, "continue", False)
+    st = nat.current_stream_ptr(dev)
+    for cap in (20000, 7001, 1):     # roomy, cut in the middle of a frame (odd: the pair path), one row
+        dec = Guarded((cap, T, 9), torch.float32, dev)
+        coords = Guarded((cap, 4), torch.int32, dev)
+        num = Guarded((cap,), torch.int32, dev)
+        vnum = Guarded((F,), torch.int32, dev)
+        voff = Guarded((F + 1,), torch.int64, dev)
+        nat.check(lib.lv_pillarize_concat(h.ptr, ctypes.byref(cfg), pts.data_ptr(), F, offs.ctypes.data, cap, 0.25, 0.25,
+                                          -49.875, -49.875, 0, 0, dec.t.data_ptr(), coords.t.data_ptr(),
+                                          num.t.data_ptr(), vnum.t.data_ptr(), voff.t.data_ptr(), st))
+        torch.cuda.synchronize()
+        for g in (dec, coords, num, vnum, voff):
+            assert g.intact(), cap
+        total = int(voff.t[F])
+        assert total == int(vnum.t.sum()) and total > 7001
+        vox = Guarded((cap, T, 4), torch.float32, dev)
+        nat.check(lib.lv_voxelize_concat(h.ptr, ctypes.byref(cfg), pts.data_ptr(), F, offs.ctypes.data, cap,
+                                         vox.t.data_ptr(), coords.t.data_ptr(), num.t.data_ptr(), vnum.t.data_ptr(),
+                                         voff.t.data_ptr(), st))
+        feats = Guarded((cap, 64), torch.float32, dev)
+        w = torch.randn((64, 9), device=dev)
+        sc, sh = torch.rand(64, device=dev) + 0.5, torch.randn(64, device=dev)
+        nat.check(lib.lv_pillarize_pfn_concat(h.ptr, ctypes.byref(cfg), pts.data_ptr(), F, offs.ctypes.data, cap, 0.25, 0.25,
+                                              -49.875, -49.875, 0, 0, w.data_ptr(), sc.data_ptr(), sh.data_ptr(), 64,
+                                              feats.t.data_ptr(), coords.t.data_ptr(), num.t.data_ptr(),
+                                              vnum.t.data_ptr(), voff.t.data_ptr(), st))
+        canvas = Guarded((F, 64, 400, 400), torch.float32, dev)
+        rows = min(total, cap)
+        nat.check(lib.lv_pillar_scatter_dev(h.ptr, feats.t.data_ptr(), coords.t.data_ptr(), voff.t[F:].data_ptr(), cap, 64,
+                                            F, 400, 400, canvas.t.data_ptr(), st))
+        torch.cuda.synchronize()
+        for g in (vox, feats, coords, num, vnum, voff, canvas):
+            assert g.intact(), cap
+        # the canvas holds exactly the kept rows
+        assert int((canvas.t.abs().sum(dim=1) > 0).sum()) <= rows
+
+
+def test_padded_voxelize_bev_and_ingest(env):
+    torch, nat, lib, h, make_cfg = env
+    dev = torch.device("cuda", 0)
+    st = nat.current_stream_ptr(dev)
+    frames = [synth.c5_frame(600)[:2049], np.zeros((0, 4), np.float32), synth.c5_frame(601)[:7000]]
+    pts = torch.from_numpy(np.concatenate(frames)).to(dev)
+    offs = np.zeros(4, np.int64)
+    offs[1:] = np.cumsum([f.shape[0] for f in frames])
+    for T, V, zero_tail in ((5, 900, True), (60, 2000, False), (3, 17, True)):
+        cfg = make_cfg(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, T, V, 4, "break", zero_tail)
+        vox = Guarded((3, V, T, 4), torch.float32, dev)
+        coords = Guarded((3, V, 3), torch.int32, dev)
+        num = Guarded((3, V), torch.int32, dev)
+        vnum = Guarded((3,), torch.int32, dev)
+        nat.check(lib.lv_voxelize(h.ptr, ctypes.byref(cfg), pts.data_ptr(), 3, offs.ctypes.data, vox.t.data_ptr(),
+                                  coords.t.data_ptr(), num.t.data_ptr(), vnum.t.data_ptr(), st))
+        torch.cuda.synchronize()
+        for g in (vox, coords, num, vnum):
+            assert g.intact(), (T, V)
+    # BEV: odd cell count (scalar finalize) and the flat4 path
+    shape3 = (ctypes.c_int32 * 3)
+    for shape in ((333, 333, 3), (336, 336, 3)):
+        cells = shape[0] * shape[1] * shape[2]
+        raw = Guarded((3, cells), torch.float32, dev)
+        nrm = Guarded((3, cells), torch.float32, dev)
+        u8 = Guarded((3, cells), torch.uint8, dev)
+        nat.check(lib.lv_bev_rasterize(h.ptr, pts.data_ptr(), 4, 3, offs.ctypes.data, None, None, 3, shape3(*shape),
+                                       (ctypes.c_double * 3)(0.4, 0.4, 1.5), -2.0, 16.0, raw.t.data_ptr(),
+                                       nrm.t.data_ptr(), u8.t.data_ptr(), None, None, st))
+        torch.cuda.synchronize()
+        for g in (raw, nrm, u8):
+            assert g.intact(), shape
+        assert int(raw.t.sum()) > 0
+    # ingest: 1023 + 1024 + 1025 rows straddle the 1024-row TMA tiles
+    raw5 = synth.load_fixture_raw()
+    sizes = [1023, 1024, 1025]
+    rows = torch.from_numpy(np.ascontiguousarray(raw5[:sum(sizes)])).to(dev)
+    soffs = np.zeros(4, np.int64)
+    soffs[1:] = np.cumsum(sizes)
+    tm = np.stack([synth.sweep_transform(s) for s in range(3)]).reshape(3, 16)
+    lag = np.array([0.0, 0.05, 0.1], np.float32)
+    for cols in (4, 5):
+        out = Guarded((sum(sizes), cols), torch.float32, dev)
+        nat.check(lib.lv_ingest_sweeps(h.ptr, rows.data_ptr(), 3, soffs.ctypes.data, tm.ctypes.data, None, lag.ctypes.data,
+                                       0, -1.0, cols, out.t.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert out.intact() and bool((out.t != SENT_F).all())
