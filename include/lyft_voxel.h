@@ -222,6 +222,16 @@ int lv_unpad_batch(lv_handle* h, const float* d_voxels, const int32_t* d_num_poi
                    float* d_out_voxels, int32_t* d_out_num_points, int32_t* d_out_coors,
                    int64_t* d_out_total, lv_stream stream);
 
+/* lv_voxelize_concat followed by SimpleVoxel.forward (second/second/pytorch/models/voxel_encoder.py:219-225)
+ * without writing the (rows, T, C) voxels: d_mean (capacity_rows, num_features_out) float32 holds
+ * sum_t voxels[p, t, c] / num_points[p] for the leading num_features_out (1..4) channels.  Needs
+ * num_features == 4.  The mean VFE of the 0.05 m SECOND configs. */
+int lv_voxelize_mean_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points,
+                            int32_t n_frames, const int64_t* h_frame_offsets, int64_t capacity_rows,
+                            int32_t num_features_out, float* d_mean, int32_t* d_coords4,
+                            int32_t* d_num_points, int32_t* d_voxel_num, int64_t* d_voxel_offsets,
+                            lv_stream stream);
+
 int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const float* h_points,
                      int32_t n_frames, const int64_t* h_frame_offsets, float* h_voxels,
                      int32_t* h_coords, int32_t* h_num_points, int32_t* h_voxel_num);

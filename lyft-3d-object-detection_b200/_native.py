@@ -77,6 +77,8 @@ SIGNATURES = {
                                           _vp, _vp]),
     "lv_pillarize_concat": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), _vp, _i32, _vp, _i64, _f32, _f32, _f32,
                                            _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lv_voxelize_mean_concat": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), _vp, _i32, _vp, _i64, _i32, _vp, _vp,
+                                               _vp, _vp, _vp, _vp]),
     "lv_unpad_batch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lv_voxelize_host": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lv_pillar_out_channels": (ctypes.c_int, [_i32, _i32, _i32]),

@@ -455,10 +455,11 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p) {
 #define VX_OUT_VOXELS 0     // raw (T,C) voxels
 #define VX_OUT_DECORATE 1   // PillarFeatureNet decoration fused into the gather, one warp per pillar
 #define VX_OUT_PFN 2        // decoration + PFNLayer (inference) fused into the gather: (rows, units) features
+#define VX_OUT_MEAN 3       // SimpleVoxel mean VFE (voxel_encoder.py:219-225) fused into the gather
 template <int MODE, bool C4>
 __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bins_kernel(VoxParams p, DecoCfg d, float* __restrict__ decorated,
                                                                 PfnCfg pfn) {
-  constexpr bool DECO = MODE != VX_OUT_VOXELS;
+  constexpr bool DECO = MODE == VX_OUT_DECORATE || MODE == VX_OUT_PFN;
   extern __shared__ __align__(16) int smem[];
   const int NV = 1 << p.low_bits;
   int* slot_tab = smem;                    // [NV][T]
@@ -570,6 +571,36 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
   const long long row0 = s_row0;
   const int32_t* ccell = p.creator_cell + (fstart - p.pt_lo);
   if (row0 + v0 + nv > p.capacity) nv = (int)(p.capacity - (row0 + v0) > 0 ? p.capacity - (row0 + v0) : 0);
+  if (MODE == VX_OUT_MEAN) {
+    // one thread per voxel: mean of its stored points (the padded slots add zeros), count, coordinates.
+    // `decorated` is the (rows, d.C_out) mean matrix, d.C_out <= 4 leading channels.
+    const float4* pts4 = reinterpret_cast<const float4*>(p.pts) + fstart;
+    for (int v = threadIdx.x; v < nv; v += VX_THREADS) {
+      int n = total[v];
+      if (n > p.T) n = p.T;
+      const long long row = row0 + v0 + v;
+      int cx, cy, cz;
+      vx_cell_coords(p, ccell[v0 + v], cz, cy, cx);
+      p.num_points[row] = n;
+      if (p.coord_cols == 4) {
+        *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(f, cz, cy, cx);  // preprocess.py:44-50
+      } else {
+        int32_t* co = p.coords + row * 3;
+        co[0] = cz; co[1] = cy; co[2] = cx;
+      }
+      const int* sl = slot_tab + v * p.T;
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = 0; t < n; ++t) {
+        const float4 q = __ldg(pts4 + sl[t]);
+        s4.x += q.x; s4.y += q.y; s4.z += q.z; s4.w += q.w;
+      }
+      const float fn = (float)n;
+      const float m4[4] = {__fdiv_rn(s4.x, fn), __fdiv_rn(s4.y, fn), __fdiv_rn(s4.z, fn), __fdiv_rn(s4.w, fn)};
+      float* o = decorated + row * d.C_out;
+      for (int c = 0; c < d.C_out; ++c) o[c] = m4[c];
+    }
+    return;
+  }
   if (MODE == VX_OUT_VOXELS && C4) {
     // 2a: one thread per voxel: count and coordinates
     const float4* pts4 = reinterpret_cast<const float4*>(p.pts) + fstart;
@@ -802,7 +833,7 @@ static int vx_set_smem(K kernel, size_t bytes) {
 static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
                   const int64_t* h_frame_offsets, float* d_voxels, int32_t* d_coords, int32_t* d_num_points,
                   int32_t* d_voxel_num, int concat, int64_t capacity, int64_t* d_row_base, const DecoCfg* deco,
-                  float* d_decorated, const PfnCfg* pfn, lv_stream stream_) {
+                  float* d_decorated, const PfnCfg* pfn, lv_stream stream_, int mean_channels = 0) {
   LV_REQUIRE(h != nullptr, "lv_voxelize: null handle");
   LV_REQUIRE(cfg && h_frame_offsets, "lv_voxelize: null config / frame offsets");
   LV_REQUIRE(n_frames >= 0, "lv_voxelize: negative frame count");
@@ -818,7 +849,10 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   LV_REQUIRE(G < (1ll << 28), "lv_voxelize: grid of %lld cells exceeds the dense-map limit (2^28)", (long long)G);
   LV_REQUIRE(n_frames == 0 || h_frame_offsets[0] == 0, "lv_voxelize: frame_offsets[0] must be 0");
   if (n_frames == 0) return LV_OK;
-  LV_REQUIRE((d_voxels || deco) && d_coords && d_num_points && d_voxel_num, "lv_voxelize: null output");
+  LV_REQUIRE((d_voxels || deco || mean_channels) && d_coords && d_num_points && d_voxel_num, "lv_voxelize: null output");
+  LV_REQUIRE(mean_channels == 0 || (d_decorated && cfg->num_features == 4 && mean_channels <= 4 &&
+                                    (reinterpret_cast<uintptr_t>(d_points) & 15) == 0),
+             "lv_voxelize_mean_concat: needs 4 features per point, 1..4 output channels and 16-byte aligned points");
   LV_REQUIRE(!deco || (d_decorated && concat && cfg->num_features == 4 && cfg->max_points <= 64 &&
                        (reinterpret_cast<uintptr_t>(d_points) & 15) == 0),
              "lv_pillarize_concat: needs 4 features per point, max_points <= 64 and 16-byte aligned points");
@@ -912,7 +946,11 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   else LV_CHECK(vx_set_smem(vx_cells_kernel<false>, p.tma_bytes));
   LV_CHECK(vx_set_smem(vx_keys_kernel, smem_keys));
   LV_CHECK(vx_set_smem(vx_scatter_kernel, smem_scatter));
-  if (pfn) LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_PFN, true>, smem_bins));
+  if (mean_channels) {
+    dcfg.C_out = mean_channels;
+    dcfg.T = T;
+    LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_MEAN, true>, smem_bins));
+  } else if (pfn) LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_PFN, true>, smem_bins));
   else if (deco) LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_DECORATE, true>, smem_bins));
   else if (out4) LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_VOXELS, true>, smem_bins));
   else LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_VOXELS, false>, smem_bins));
@@ -963,7 +1001,8 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     }
     {
       dim3 grid_b((unsigned)n_bins, (unsigned)nf);
-      if (pfn) vx_bins_kernel<VX_OUT_PFN, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, d_decorated, pcfg);
+      if (mean_channels) vx_bins_kernel<VX_OUT_MEAN, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, d_decorated, pcfg);
+      else if (pfn) vx_bins_kernel<VX_OUT_PFN, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, d_decorated, pcfg);
       else if (deco) vx_bins_kernel<VX_OUT_DECORATE, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, d_decorated, pcfg);
       else if (out4) vx_bins_kernel<VX_OUT_VOXELS, true><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, nullptr, pcfg);
       else vx_bins_kernel<VX_OUT_VOXELS, false><<<grid_b, VX_THREADS, smem_bins, stream>>>(p, dcfg, nullptr, pcfg);
@@ -1090,4 +1129,16 @@ extern "C" int lv_unpad_batch(lv_handle* h, const float* d_voxels, const int32_t
       d_out_voxels, d_out_num_points, d_out_coors, d_out_total);
   LV_LAUNCH_CHECK(h);
   return LV_OK;
+}
+
+extern "C" int lv_voxelize_mean_concat(lv_handle* h, const lv_voxel_config* cfg, const float* d_points, int32_t n_frames,
+                                       const int64_t* h_frame_offsets, int64_t capacity_rows, int32_t num_features_out,
+                                       float* d_mean, int32_t* d_coords4, int32_t* d_num_points, int32_t* d_voxel_num,
+                                       int64_t* d_voxel_offsets, lv_stream stream) {
+  LV_REQUIRE(cfg != nullptr, "lv_voxelize_mean_concat: null config");
+  LV_REQUIRE(capacity_rows >= 0, "lv_voxelize_mean_concat: negative capacity");
+  LV_REQUIRE(n_frames == 0 || d_voxel_offsets, "lv_voxelize_mean_concat: null voxel_offsets");
+  LV_REQUIRE(num_features_out >= 1 && num_features_out <= 4, "lv_voxelize_mean_concat: num_features_out must be 1..4");
+  return vx_run(h, cfg, d_points, n_frames, h_frame_offsets, nullptr, d_coords4, d_num_points, d_voxel_num, 1,
+                capacity_rows, d_voxel_offsets, nullptr, d_mean, nullptr, stream, num_features_out);
 }

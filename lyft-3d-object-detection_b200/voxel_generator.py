@@ -202,3 +202,34 @@ def unpad_multigpu_batch(voxels, num_points, coordinates, num_voxels):
                                      nat.current_stream_ptr(dev)))
     n = int(total.item())
     return out_v[:n], out_n[:n], out_c[:n]
+
+
+def voxelize_mean_frames(points, frame_offsets, voxel_size, coors_range, max_points, max_voxels,
+                         num_features_out=4, overflow="continue", capacity=None, handle=None):
+    """Voxelization + SimpleVoxel mean VFE in one pipeline (lv_voxelize_mean_concat): the (V,T,C)
+    voxel tensor of ``generate`` + ``SimpleVoxel.forward`` (voxel_encoder.py:219-225) is never
+    written.  points: (N_total, 4) float32 CUDA tensor; returns CUDA tensors
+    (mean (sum V, num_features_out), coordinates (sum V, 4) [b,z,y,x], num_points (sum V),
+    voxel_num (F))."""
+    import torch
+    lib = nat.load()
+    if not (_is_cuda_tensor(points) and points.dtype == torch.float32 and points.dim() == 2 and points.shape[1] == 4):
+        raise ValueError("points must be a (N, 4) float32 CUDA tensor")
+    pts = points.contiguous()
+    offs = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+    F = offs.shape[0] - 1
+    cap = int(capacity if capacity is not None else F * int(max_voxels))
+    dev = pts.device
+    cfg = _make_config(voxel_size, coors_range, int(max_points), int(max_voxels), 4, overflow, False)
+    mean = torch.empty((cap, num_features_out), dtype=torch.float32, device=dev)
+    coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((cap,), dtype=torch.int32, device=dev)
+    vnum = torch.empty((F,), dtype=torch.int32, device=dev)
+    voff = torch.empty((F + 1,), dtype=torch.int64, device=dev)
+    h = handle or nat.get_handle(dev.index)
+    with torch.cuda.device(dev):
+        nat.check(lib.lv_voxelize_mean_concat(h.ptr, ctypes.byref(cfg), pts.data_ptr(), F, offs.ctypes.data, cap,
+                                              int(num_features_out), mean.data_ptr(), coords.data_ptr(), num.data_ptr(),
+                                              vnum.data_ptr(), voff.data_ptr(), nat.current_stream_ptr(dev)))
+    total = min(int(voff[F].item()), cap)
+    return mean[:total], coords[:total], num[:total], vnum

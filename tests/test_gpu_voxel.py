@@ -240,3 +240,27 @@ def test_unpad_multigpu_batch_equals_voxelnet_forward(vg, vo):
     ref_c = torch.cat([coors[i, :k] for i, k in enumerate(nv.tolist())], dim=0)
     assert v2.shape == ref_v.shape and bool((v2.view(torch.int32) == ref_v.view(torch.int32)).all())
     assert bool((n2 == ref_n).all()) and bool((c2 == ref_c).all())
+
+
+@pytest.mark.parametrize("cout", [4, 3])
+def test_fused_mean_vfe_second_config(vg, vo, cloud11, cout):
+    """C2 (0.05 m SECOND voxels, T=5, V=60000): voxelize + SimpleVoxel mean in one pipeline vs
+    oracle voxelizer -> oracle SimpleVoxel (voxel_encoder.py:219-225)."""
+    import torch
+    from oracle import pillar_oracle as po
+    frames = [cloud11[:200000], cloud11[200000:260000]]
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    offs = np.array([0, 200000, 260000], dtype=np.int64)
+    mean, coords, num, vnum = vg.voxelize_mean_frames(pts, offs, synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE,
+                                                      synth.SECOND_MAX_POINTS, synth.SECOND_MAX_VOXELS, cout)
+    at = 0
+    for b, fr in enumerate(frames):
+        v, c, n = vo.points_to_voxel(fr, synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, synth.SECOND_MAX_POINTS,
+                                     synth.SECOND_MAX_VOXELS)
+        k = v.shape[0]
+        assert int(vnum[b]) == k
+        assert np.array_equal(coords[at:at + k, 1:].cpu().numpy(), c) and bool((coords[at:at + k, 0] == b).all())
+        assert np.array_equal(num[at:at + k].cpu().numpy(), n)
+        np.testing.assert_allclose(mean[at:at + k].cpu().numpy(), po.simple_voxel_mean(v, n, cout), rtol=1e-6, atol=1e-6)
+        at += k
+    assert at == mean.shape[0]
