@@ -164,7 +164,10 @@ class PipelinedEngine:
         s_sc  (low)   scatter(i) waits for s_vox(i)   <- buffer set i % 2, pillar count read on the
                                                          device (lv_pillar_scatter_dev)
 
-    so scatter(i) overlaps BEV(i+1) and the voxelizer of step i+1.  Results are identical to
+    so scatter(i) may overlap BEV(i+1) and the voxelizer of step i+1.  Measured (profiles/README.md):
+    1.855 ms per step with the host read, 1.816 ms without it on one stream, 1.755 ms on three
+    streams - most of the gain is the missing host round trip, kernels of different streams
+    overlap little because the canvas kernel fills every SM.  Results are identical to
     FrameBatchEngine.step (tests/test_gpu_engine.py); set 0 aliases the engine's own buffers.
     """
 
