@@ -27,6 +27,18 @@ def shard_frames(n_frames, rank, world_size):
     return list(range(rank, n_frames, world_size))
 
 
+# A/B knobs of the library (lv_set_option), settable from the environment for measurement runs
+ENV_OPTIONS = {"LV_VOX_MAP_MB": ("vox_dense_map_limit_bytes", 1 << 20), "LV_BEV_TMA": ("bev_tma", 1),
+               "LV_DISABLE_TMA": ("disable_tma", 1), "LV_BEV_FIF": ("bev_frames_in_flight", 1)}
+
+
+def apply_env_options(handle):
+    import os
+    for env, (name, scale) in ENV_OPTIONS.items():
+        if os.environ.get(env):
+            handle.set_option(name, int(os.environ[env]) * scale)
+
+
 class FrameBatchEngine:
     def __init__(self, device, frames_per_step, points_per_frame,
                  bev_shape=synth.BEV_SHAPE, bev_voxel_size=synth.BEV_VOXEL_SIZE, bev_z_offset=synth.BEV_Z_OFFSET,
@@ -38,15 +50,7 @@ class FrameBatchEngine:
         self.lib = nat.load()
         self.dev = torch.device("cuda", device)
         self.h = nat.get_handle(device)
-        import os as _os
-        if _os.environ.get("LV_VOX_MAP_MB"):
-            self.h.set_option("vox_dense_map_limit_bytes", int(_os.environ["LV_VOX_MAP_MB"]) << 20)
-        if _os.environ.get("LV_BEV_TMA"):
-            self.h.set_option("bev_tma", int(_os.environ["LV_BEV_TMA"]))
-        if _os.environ.get("LV_DISABLE_TMA"):
-            self.h.set_option("disable_tma", int(_os.environ["LV_DISABLE_TMA"]))
-        if _os.environ.get("LV_BEV_FIF"):
-            self.h.set_option("bev_frames_in_flight", int(_os.environ["LV_BEV_FIF"]))
+        apply_env_options(self.h)
         self.F = int(frames_per_step)
         self.n = int(points_per_frame)
         self.bev_shape = tuple(int(s) for s in bev_shape)
@@ -172,12 +176,8 @@ class PipelinedEngine:
     """
 
     def __init__(self, engine, bev_priority=-1, vox_priority=-1, scatter_priority=0):
-        import os as _os
         e = self.eng = engine
         d = e.dev
-        bev_priority = int(_os.environ.get("LV_PIPE_BEV_PRIO", bev_priority))
-        vox_priority = int(_os.environ.get("LV_PIPE_VOX_PRIO", vox_priority))
-        scatter_priority = int(_os.environ.get("LV_PIPE_SC_PRIO", scatter_priority))
         self.s_bev = torch.cuda.Stream(d, priority=bev_priority)
         self.s_vox = torch.cuda.Stream(d, priority=vox_priority)
         self.s_sc = torch.cuda.Stream(d, priority=scatter_priority)
