@@ -215,16 +215,20 @@ __global__ void __launch_bounds__(VX_THREADS) vx_assign_kernel(VoxParams p) {
   int cell[VX_ITEMS];
   unsigned flags = 0;
   int s = 0;
+  // two batches of independent loads: the eight cells, then the eight first[] entries
 #pragma unroll
   for (int k = 0; k < VX_ITEMS; ++k) {
     const int li = base + k;
-    cell[k] = -1;
-    if (li < L.n) {
-      cell[k] = p.cell[L.start + li - p.pt_lo];
-      if (cell[k] >= 0 && map[cell[k]] == li) {
-        flags |= 1u << k;
-        ++s;
-      }
+    cell[k] = li < L.n ? p.cell[L.start + li - p.pt_lo] : -1;
+  }
+  int first[VX_ITEMS];
+#pragma unroll
+  for (int k = 0; k < VX_ITEMS; ++k) first[k] = cell[k] >= 0 ? map[cell[k]] : -1;
+#pragma unroll
+  for (int k = 0; k < VX_ITEMS; ++k) {
+    if (cell[k] >= 0 && first[k] == base + k) {
+      flags |= 1u << k;
+      ++s;
     }
   }
   int inc = s;
@@ -306,18 +310,22 @@ __global__ void __launch_bounds__(VX_THREADS) vx_keys_kernel(VoxParams p) {
   const int cut = p.frame_cut[L.fl];
   const int base = L.c * VX_CHUNK;
   const int lane = threadIdx.x & 31;
-#pragma unroll 2
+  // two batches of independent loads: the eight cells, then the eight voxel ids
+  int craw[VX_ITEMS], vid[VX_ITEMS];
+#pragma unroll
+  for (int k = 0; k < VX_ITEMS; ++k) {
+    const int li = base + k * VX_THREADS + threadIdx.x;
+    craw[k] = li < L.n ? p.cell[L.start + li - p.pt_lo] : -1;
+  }
+#pragma unroll
+  for (int k = 0; k < VX_ITEMS; ++k) vid[k] = craw[k] >= 0 ? ~map[craw[k] & ~VX_CREATOR_BIT] : 0x7fffffff;
+#pragma unroll
   for (int k = 0; k < VX_ITEMS; ++k) {
     const int li = base + k * VX_THREADS + threadIdx.x;
     unsigned key = VX_DROPPED;
     if (li < L.n) {
-      const int64_t wi = L.start + li - p.pt_lo;
-      const int craw = p.cell[wi];
-      if (craw >= 0) {
-        const int vid = ~map[craw & ~VX_CREATOR_BIT];
-        if (vid < p.V && li < cut) key = (unsigned)vid;
-      }
-      p.key0[wi] = key;
+      if (vid[k] < p.V && li < cut) key = (unsigned)vid[k];
+      p.key0[L.start + li - p.pt_lo] = key;
     }
     const unsigned digit = key == VX_DROPPED ? 0xffffffffu : (key >> p.low_bits);
     const unsigned peers = __match_any_sync(0xffffffffu, digit);
@@ -403,17 +411,23 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p) {
   int rnk[VX_ITEMS];
   const int base = L.c * VX_CHUNK + warp * (32 * VX_ITEMS);
   const unsigned lt = lv_lanemask_lt();
+  // all sixteen loads first (keys and cells), then the touched-cell reset: K3 was the last
+  // reader of first[]
+  {
+    int craw[VX_ITEMS];
+#pragma unroll
+    for (int r = 0; r < VX_ITEMS; ++r) {
+      const int li = base + r * 32 + lane;
+      const int64_t wi = L.start + li - p.pt_lo;
+      key[r] = li < L.n ? p.key0[wi] : VX_DROPPED;
+      craw[r] = li < L.n ? p.cell[wi] : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < VX_ITEMS; ++r)
+      if (craw[r] >= 0 && (craw[r] & VX_CREATOR_BIT)) map[craw[r] & ~VX_CREATOR_BIT] = VX_EMPTY;
+  }
 #pragma unroll
   for (int r = 0; r < VX_ITEMS; ++r) {
-    const int li = base + r * 32 + lane;
-    key[r] = VX_DROPPED;
-    if (li < L.n) {
-      const int64_t wi = L.start + li - p.pt_lo;
-      key[r] = p.key0[wi];
-      const int craw = p.cell[wi];
-      // touched-cell reset: K3 was the last reader of first[]
-      if (craw >= 0 && (craw & VX_CREATOR_BIT)) map[craw & ~VX_CREATOR_BIT] = VX_EMPTY;
-    }
     const bool live = key[r] != VX_DROPPED;
     const unsigned digit = live ? (key[r] >> p.low_bits) : 0xffffffffu;
     const unsigned peers = __match_any_sync(0xffffffffu, digit);
