@@ -85,7 +85,7 @@ struct lv_handle {
   lv_buffer vox_map;                  // i32 [frames_in_flight][grid cells], kept all-INT_MAX between calls
   lv_buffer vox_cell, vox_aux, vox_keys[2], vox_vals[2], vox_hist, vox_chunk, vox_frame_state;
   lv_buffer vox_row_base;
-  lv_mirror vox_frame_offsets, vox_chunk_table;
+  lv_mirror vox_frame_offsets, vox_chunk_table, vox_chunk_frame;
   lv_buffer vox_stage_points, vox_stage_out[4];
 
   // pillar
@@ -101,7 +101,7 @@ inline std::vector<lv_buffer*> lv_all_buffers(lv_handle* h) {
           &h->bev_stage_out[0], &h->bev_stage_out[1], &h->bev_stage_out[2], &h->bev_stage_out[3], &h->bev_stage_out[4],
           &h->bev_stage_map, &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1], &h->vox_vals[0],
           &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state, &h->vox_row_base,
-          &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_stage_points, &h->vox_stage_out[0],
+          &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_chunk_frame.dev, &h->vox_stage_points, &h->vox_stage_out[0],
           &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3], &h->pil_map, &h->ing_offsets.dev,
           &h->ing_tm.dev, &h->ing_lag.dev, &h->ing_has.dev};
 }

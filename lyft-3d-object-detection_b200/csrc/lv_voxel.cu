@@ -56,6 +56,7 @@ struct VoxParams {
   int C;
   const int64_t* frame_off;    // device [F+1] global point offsets
   const int32_t* frame_chunk;  // device [F+1] chunk prefix
+  const int32_t* chunk_frame;  // device [chunks] frame of every chunk
   int f0, f1;                  // frames of this sub-batch
   int chunk_lo;                // first chunk of the sub-batch (global chunk id)
   int64_t pt_lo;               // first point of the sub-batch (global point index)
@@ -104,20 +105,11 @@ __device__ __forceinline__ void vx_cell_coords(const VoxParams& p, int c, int& c
   cx = rem - cy * p.grid[0];
 }
 
-// One thread resolves the frame of the CTA's chunk by binary search, then broadcasts.
-__device__ __forceinline__ ChunkLoc vx_locate(const VoxParams& p, int* smem4) {
-  if (threadIdx.x == 0) {
-    const int g = p.chunk_lo + blockIdx.x;
-    int lo = p.f0, hi = p.f1;  // frame_chunk[lo] <= g < frame_chunk[hi]
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(p.frame_chunk + mid) <= g) lo = mid; else hi = mid;
-    }
-    smem4[0] = lo;
-  }
-  __syncthreads();
+// Frame of the CTA's chunk: one broadcast read of the host-built chunk -> frame table (no search,
+// no barrier).
+__device__ __forceinline__ ChunkLoc vx_locate(const VoxParams& p) {
   ChunkLoc L;
-  L.f = smem4[0];
+  L.f = __ldg(p.chunk_frame + p.chunk_lo + blockIdx.x);
   L.fl = L.f - p.f0;
   const int cb = __ldg(p.frame_chunk + L.f);
   L.c = p.chunk_lo + blockIdx.x - cb;
@@ -134,8 +126,7 @@ template <bool C4>
 __global__ void __launch_bounds__(VX_THREADS) vx_cells_kernel(VoxParams p) {
   extern __shared__ __align__(128) float tile[];  // [VX_CHUNK][C] when p.tma_bytes != 0
   __shared__ __align__(8) uint64_t bar;
-  __shared__ int sm[4];
-  const ChunkLoc L = vx_locate(p, sm);
+  const ChunkLoc L = vx_locate(p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* src = p.pts + (L.start + (int64_t)L.c * VX_CHUNK) * p.C;
   const bool staged = p.tma_bytes != 0 && (L.c + 1) * VX_CHUNK <= L.n && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
@@ -204,10 +195,9 @@ __device__ __forceinline__ void vx_st_state(unsigned long long* p, unsigned long
 }
 
 __global__ void __launch_bounds__(VX_THREADS) vx_assign_kernel(VoxParams p) {
-  __shared__ int sm[4];
   __shared__ int sw[VX_WARPS];
   __shared__ int s_excl;
-  const ChunkLoc L = vx_locate(p, sm);
+  const ChunkLoc L = vx_locate(p);
   int32_t* map = p.map + (int64_t)L.fl * p.G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // thread-contiguous items: thread t owns local points base + t*8 .. +7 (index order)
@@ -300,9 +290,8 @@ __global__ void __launch_bounds__(VX_THREADS) vx_assign_kernel(VoxParams p) {
 
 // ---------------------------------------------------------------- K3: keys + bin histogram
 __global__ void __launch_bounds__(VX_THREADS) vx_keys_kernel(VoxParams p) {
-  __shared__ int sm[4];
   extern __shared__ int hist[];  // [n_bins]
-  const ChunkLoc L = vx_locate(p, sm);
+  const ChunkLoc L = vx_locate(p);
   const int32_t* map = p.map + (int64_t)L.fl * p.G;
   const int D = p.n_bins;
   for (int d = threadIdx.x; d < D; d += VX_THREADS) hist[d] = 0;
@@ -398,9 +387,8 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scan_hist_kernel(VoxParams p) {
 // after the rounds an exclusive scan over the warps (plus the scanned global table) turns
 // them into the warp's base for each bin.
 __global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p) {
-  __shared__ int sm[4];
   extern __shared__ int cnt[];  // [8][n_bins]
-  const ChunkLoc L = vx_locate(p, sm);
+  const ChunkLoc L = vx_locate(p);
   const int D = p.n_bins;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < VX_WARPS * D; i += VX_THREADS) cnt[i] = 0;
@@ -905,6 +893,11 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   const void *d_off = nullptr, *d_chunk = nullptr;
   LV_CHECK(h->vox_frame_offsets.sync(h_frame_offsets, sizeof(int64_t) * (n_frames + 1), stream, &d_off));
   LV_CHECK(h->vox_chunk_table.sync(frame_chunk.data(), sizeof(int32_t) * (n_frames + 1), stream, &d_chunk));
+  std::vector<int32_t> chunk_frame((size_t)frame_chunk[n_frames] + 1, 0);
+  for (int f = 0; f < n_frames; ++f)
+    for (int32_t c = frame_chunk[f]; c < frame_chunk[f + 1]; ++c) chunk_frame[c] = f;
+  const void* d_chunk_frame = nullptr;
+  LV_CHECK(h->vox_chunk_frame.sync(chunk_frame.data(), sizeof(int32_t) * chunk_frame.size(), stream, &d_chunk_frame));
 
   // sub-batches: bounded by the dense map budget (L2 residency) and by the point workspace,
   // then balanced so that no launch is a small remainder
@@ -922,6 +915,7 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   p.pts = d_points; p.C = C;
   p.frame_off = (const int64_t*)d_off;
   p.frame_chunk = (const int32_t*)d_chunk;
+  p.chunk_frame = (const int32_t*)d_chunk_frame;
   for (int j = 0; j < 3; ++j) {
     p.lo[j] = cfg->coors_range[j];
     p.vs[j] = cfg->voxel_size[j];
