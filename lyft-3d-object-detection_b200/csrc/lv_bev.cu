@@ -130,24 +130,34 @@ __global__ void __launch_bounds__(BEV_THREADS) bev_hist_kernel(BevParams p) {
       phase ^= 1u << s;
     }
     const float* buf = tiles + (size_t)s * TILE_FLOATS;
+    // the thread's points of this tile, all loads in flight before the first one is used
+    float px[BEV_ITEMS], py[BEV_ITEMS], pz[BEV_ITEMS];
+#pragma unroll
+    for (int r = 0; r < BEV_ITEMS; ++r) {
+      const int li = warp * BEV_WTILE + r * 32 + lane;
+      const int64_t i = t * BEV_TILE + li;
+      px[r] = py[r] = pz[r] = 0.f;
+      if (i >= v0 && i < v1) {
+        if (STRIDE == 4) {
+          float4 v;
+          if (in_smem) v = reinterpret_cast<const float4*>(buf)[li];
+          else v = lv_ld_stream_f4(reinterpret_cast<const float4*>(p.pts) + i);
+          px[r] = v.x; py[r] = v.y; pz[r] = v.z;
+        } else if (STRIDE != 0 && in_smem) {
+          px[r] = buf[li * STRIDE]; py[r] = buf[li * STRIDE + 1]; pz[r] = buf[li * STRIDE + 2];
+        } else {
+          const float* q = p.pts + i * p.stride;
+          px[r] = __ldg(q); py[r] = __ldg(q + 1); pz[r] = __ldg(q + 2);
+        }
+      }
+    }
 #pragma unroll
     for (int r = 0; r < BEV_ITEMS; ++r) {
       const int li = warp * BEV_WTILE + r * 32 + lane;
       const int64_t i = t * BEV_TILE + li;
       unsigned key = 0xffffffffu;
       if (i >= v0 && i < v1) {
-        float x, y, z;
-        if (STRIDE == 4) {
-          float4 v;
-          if (in_smem) v = reinterpret_cast<const float4*>(buf)[li];
-          else v = lv_ld_stream_f4(reinterpret_cast<const float4*>(p.pts) + i);
-          x = v.x; y = v.y; z = v.z;
-        } else if (STRIDE != 0 && in_smem) {
-          x = buf[li * STRIDE]; y = buf[li * STRIDE + 1]; z = buf[li * STRIDE + 2];
-        } else {
-          const float* q = p.pts + i * p.stride;
-          x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
-        }
+        float x = px[r], y = py[r], z = pz[r];
         int seg = sa;
         if (sb != sa) seg = bev_find_segment(p.seg_offsets, sa, sb + 1, i);
         if (p.seg_tm) {
