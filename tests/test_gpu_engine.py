@@ -136,3 +136,32 @@ def test_pipelined_engine_equals_serial_steps():
     rows, u8, canvas, coords, dec = want[-1]
     assert bool((eng.canvas == canvas).all()) and bool((eng.bev_u8 == u8).all())
     assert bool((st["coords"][:rows] == coords).all())
+
+
+def test_sub_batching_gives_identical_results():
+    """Workspace budgets split a batch into sub-batches (dense-map limit for the voxelizer, frames in
+    flight for the BEV counts); the outputs - including the running row offsets of the
+    concatenated layout across sub-batch borders - must not change."""
+    import torch
+    from lyft3d_b200 import _native as nat
+    from lyft3d_b200.engine import FrameBatchEngine
+    F = 7
+    frames = [synth.c5_frame(700 + f)[: 20000 + 3000 * f] for f in range(F)]
+    n = 20000
+    pts = torch.from_numpy(np.concatenate([fr[:n] for fr in frames])).cuda()
+    eng = FrameBatchEngine(0, F, n)
+    h = nat.get_handle(0)
+    eng.step(pts)
+    want = (eng.total_rows, eng.bev_u8.clone(), eng.bev_norm.clone(), eng.coords[:eng.total_rows].clone(),
+            eng.decorated[:eng.total_rows].clone(), eng.voxel_offsets.clone(), eng.canvas.clone())
+    try:
+        h.set_option("vox_dense_map_limit_bytes", 2 * 400 * 400 * 4)      # two frames per sub-batch
+        h.set_option("bev_frames_in_flight", 3)
+        rows = eng.step(pts)
+    finally:
+        h.set_option("vox_dense_map_limit_bytes", 0)
+        h.set_option("bev_frames_in_flight", 0)
+    assert rows == want[0]
+    assert bool((eng.bev_u8 == want[1]).all()) and bool((eng.bev_norm == want[2]).all())
+    assert bool((eng.coords[:rows] == want[3]).all()) and bool((eng.decorated[:rows] == want[4]).all())
+    assert bool((eng.voxel_offsets == want[5]).all()) and bool((eng.canvas == want[6]).all())
