@@ -165,3 +165,70 @@ def test_sub_batching_gives_identical_results():
     assert bool((eng.bev_u8 == want[1]).all()) and bool((eng.bev_norm == want[2]).all())
     assert bool((eng.coords[:rows] == want[3]).all()) and bool((eng.decorated[:rows] == want[4]).all())
     assert bool((eng.voxel_offsets == want[5]).all()) and bool((eng.canvas == want[6]).all())
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[4] at bench size (128 frames x 53,146 points per step): size-independent
+    properties checked against an independent torch computation on the same device.
+      BEV      per-frame sum of the raw counts == number of points whose truncated fp64 voxel
+               coordinates are in bounds; u8 == rint(clip(raw/16)*255)
+      pillars  voxel_num[f] == min(#distinct in-range cells of frame f, V); coordinates unique per
+               frame; row 0 of a frame is the cell of its first in-range point (first-come order);
+               sum(num_points) == in-range points when no pillar overflows T
+      canvas   exactly one non-zero column per pillar (features are non-zero)"""
+    import torch
+    from lyft3d_b200.engine import FrameBatchEngine
+    F = 128
+    base = np.concatenate([synth.c5_frame(800 + f) for f in range(8)])
+    n = base.shape[0] // 8
+    host = np.tile(base, (F // 8, 1))
+    # make the 128 frames distinct: a per-frame shift of x
+    host = host.reshape(F, n, 4).copy()
+    host[:, :, 0] += (np.arange(F, dtype=np.float32) * 0.03)[:, None]
+    pts = torch.from_numpy(host.reshape(F * n, 4)).cuda()
+    eng = FrameBatchEngine(0, F, n)
+    eng.features.uniform_(0.5, 1.5)
+    raw = torch.empty((F,) + eng.bev_shape, dtype=torch.float32, device="cuda")
+    from lyft3d_b200 import bev
+    bev.rasterize_frames(pts, eng.offsets, synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE, synth.BEV_Z_OFFSET, want=("raw",),
+                         out={"raw": raw})
+    rows = eng.step(pts)
+    p3 = pts.view(F, n, 4)[:, :, :3].double()
+    vs = torch.tensor(synth.BEV_VOXEL_SIZE, dtype=torch.float64, device="cuda")
+    m = 1.0 / vs
+    t = torch.tensor([synth.BEV_SHAPE[0] / 2, synth.BEV_SHAPE[1] / 2, synth.BEV_SHAPE[2] / 2], dtype=torch.float64,
+                     device="cuda") + torch.tensor([0.0, 0.0, synth.BEV_Z_OFFSET], dtype=torch.float64, device="cuda") / vs
+    u = (p3 * m) + t                                   # un-fused multiply then add, float64
+    c = torch.trunc(u)
+    shp = torch.tensor(synth.BEV_SHAPE, dtype=torch.float64, device="cuda")
+    inb = ((c >= 0) & (c < shp)).all(dim=2)
+    assert torch.equal(raw.sum(dim=(1, 2, 3)).double(), inb.sum(dim=1).double())
+    want_u8 = torch.round(torch.clamp(raw / 16.0, 0, 1) * 255).to(torch.uint8)
+    assert torch.equal(eng.bev_u8, want_u8)
+    # pillars
+    lo = torch.tensor(synth.PILLAR_RANGE[:3], dtype=torch.float32, device="cuda")
+    pv = torch.tensor(synth.PILLAR_VOXEL_SIZE, dtype=torch.float32, device="cuda")
+    cf = torch.floor((pts.view(F, n, 4)[:, :, :3] - lo) / pv)
+    grid = torch.tensor([400.0, 400.0, 1.0], device="cuda")
+    ok = ((cf >= 0) & (cf < grid)).all(dim=2)
+    cell = (cf[:, :, 1] * 400 + cf[:, :, 0]).long()
+    vnum = eng.voxel_num.cpu().numpy()
+    off = eng.voxel_offsets.cpu().numpy()
+    assert int(off[F]) == rows == int(vnum.sum())
+    total_kept = 0
+    for f in (0, 1, 63, 127):
+        cells_f = cell[f][ok[f]]
+        uniq = torch.unique(cells_f)
+        assert vnum[f] == min(int(uniq.numel()), eng.V)
+        co = eng.coords[off[f]:off[f + 1]]
+        assert bool((co[:, 0] == f).all())
+        lin = co[:, 2].long() * 400 + co[:, 3].long()
+        assert int(torch.unique(lin).numel()) == int(lin.numel())           # unique per frame
+        assert int(lin[0]) == int(cells_f[0])                                # first-come order
+        assert set(lin.tolist()) == set(uniq.tolist())
+        nump = eng.num_points[off[f]:off[f + 1]]
+        counts = torch.bincount(cells_f, minlength=160000)[lin]
+        assert torch.equal(nump.long(), torch.clamp(counts, max=eng.T))
+        total_kept += int(nump.sum())
+    nz = (eng.canvas.abs().sum(dim=1) > 0).sum()
+    assert int(nz) == rows
