@@ -128,8 +128,8 @@ def make_pool_frames(n_frames, device, seed):
 
 
 def time_other_configs(dev, reps=10):
-    """BASELINE.json configs[1..3] as single-cloud latencies (CUDA events, median of `reps`, inputs
-    resident on the device; the headline workload is configs[4])."""
+    """BASELINE.json configs[0..3] as single-cloud latencies (configs[1..3]: CUDA events, median of
+    `reps`, inputs resident on the device; the headline workload is configs[4])."""
     import numpy as np
     import torch
     from lyft3d_b200 import bev, synth, voxel_generator as vg
@@ -148,10 +148,27 @@ def time_other_configs(dev, reps=10):
             ms.append(a.elapsed_time(b))
         return float(np.median(ms))
 
+    out = {}
+    # C1: the reference's own CPU-runnable case through the drop-in call, numpy in -> numpy out
+    # (H2D, kernels, D2H and the synchronisation inside the call), wall clock; the CPU port beside it
+    import time as _time
+    from oracle import bev_oracle
+    p4 = synth.fixture_points_4xn()
+    for _ in range(3):
+        bev.create_voxel_pointcloud(p4, synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE, synth.BEV_Z_OFFSET)
+    t0 = _time.perf_counter()
+    for _ in range(reps):
+        bev.create_voxel_pointcloud(p4, synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE, synth.BEV_Z_OFFSET)
+    c1_ms = (_time.perf_counter() - t0) / reps * 1e3
+    t0 = _time.perf_counter()
+    for _ in range(3):
+        bev_oracle.create_voxel_pointcloud(p4, synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE, synth.BEV_Z_OFFSET)
+    cpu_ms = (_time.perf_counter() - t0) / 3 * 1e3
+    out["C1 create_voxel_pointcloud on the bundled sweep, drop-in call with host buffers"] = {
+        "points": int(p4.shape[1]), "ms": round(c1_ms, 4), "cpu_port_ms": round(cpu_ms, 3)}
     cloud = torch.from_numpy(synth.multisweep_cloud(20)).to(dev)       # 1,062,920 points, 10+ sweeps
     n = int(cloud.shape[0])
     offs = np.array([0, n], dtype=np.int64)
-    out = {}
     for name, vs, rg, T, V in (("C2 SECOND 0.05 m voxels, T=5, V=60000", synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, 60000),
                                ("C3 pillars 0.25 m, T=60, V=30000", synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)):
         ms = timed(lambda: vg.voxelize_frames(cloud, offs, vs, rg, T, V, zero_tail=False))
