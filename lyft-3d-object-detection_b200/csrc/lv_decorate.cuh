@@ -125,8 +125,8 @@ __device__ __forceinline__ void lv_decorate_warp(const float4 a, const float4 b,
 // the result is bit-identical.  `st` is the half's own stage, `dst` the half's own output row;
 // the caller has already issued lv_decorate_zero_tail for both rows.  Needs T > 16 (padding slots
 // exist, which is what makes the z range of the RadiusHeight variant include 0).
-__device__ __forceinline__ void lv_decorate_half(const float4 a, int num, int coor_y, int coor_x, const DecoCfg& d,
-                                                 float* st, float* __restrict__ dst, int lane) {
+__device__ __forceinline__ void lv_decorate_half_stage(const float4 a, int num, int coor_y, int coor_x, const DecoCfg& d,
+                                                       float* st, int lane, int slot_stride) {
   const int sub = lane & 15;
   float sx = a.x, sy = a.y, sz = a.z;
 #pragma unroll
@@ -149,10 +149,17 @@ __device__ __forceinline__ void lv_decorate_half(const float4 a, int num, int co
   }
   const float cx = __fadd_rn(__fmul_rn((float)coor_x, d.vx), d.x_off);
   const float cy = __fadd_rn(__fmul_rn((float)coor_y, d.vy), d.y_off);
-  if (sub < num) lv_decorate_slot(a, mx, my, mz, cx, cy, height, d, st + sub * d.C_out);
-  const int nd = num * d.C_out;
+  if (sub < num) lv_decorate_slot(a, mx, my, mz, cx, cy, height, d, st + sub * slot_stride);
+  const int nd = num * slot_stride;
   if (sub < (((nd + 3) >> 2) << 2) - nd) st[nd + sub] = 0.f;  // pad the last quad of the data part
   __syncwarp();
+}
+
+__device__ __forceinline__ void lv_decorate_half(const float4 a, int num, int coor_y, int coor_x, const DecoCfg& d,
+                                                 float* st, float* __restrict__ dst, int lane) {
+  const int sub = lane & 15;
+  lv_decorate_half_stage(a, num, coor_y, coor_x, d, st, lane, d.C_out);
+  const int nd = num * d.C_out;
   if (lv_row_vec4(d, dst)) {
     const float4* s4 = reinterpret_cast<const float4*>(st);
     float4* d4 = reinterpret_cast<float4*>(dst);

@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
       if (n1 > p.T) n1 = p.T;
       const int* sl = slot_tab + v * p.T;
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (MODE == VX_OUT_DECORATE && two && n0 <= 16 && n1 <= 16 && p.T > 16) {
+      if (two && n0 <= 16 && n1 <= 16 && p.T > 16) {
         // two small pillars (the common case: 5.4 points per pillar on a Lyft sweep) share the warp
         const int hi = lane >> 4, sub = lane & 15;
         const int nm = hi ? n1 : n0;
@@ -663,15 +663,24 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
         if (sub < nm) a = __ldg(pts4 + sl[hi * p.T + sub]);
         const int cm = ccell[v0 + v + hi];
         float* dst0 = decorated + row * per;
-        lv_decorate_zero_tail(n0, d, dst0, lane);
-        lv_decorate_zero_tail(n1, d, dst0 + per, lane);
+        if (MODE == VX_OUT_DECORATE) {
+          lv_decorate_zero_tail(n0, d, dst0, lane);
+          lv_decorate_zero_tail(n1, d, dst0 + per, lane);
+        }
         int cx, cy, cz;
         vx_cell_coords(p, cm, cz, cy, cx);
         if (sub == 0) {
           p.num_points[row + hi] = nm;
           *reinterpret_cast<int4*>(p.coords + (row + hi) * 4) = make_int4(f, cz, cy, cx);  // preprocess.py:44-50
         }
-        lv_decorate_half(a, nm, cy, cx, d, st + hi * (16 * d.C_out + 4), dst0 + hi * per, lane);
+        if (MODE == VX_OUT_DECORATE) {
+          lv_decorate_half(a, nm, cy, cx, d, st + hi * (16 * d.C_out + 4), dst0 + hi * per, lane);
+        } else {  // VX_OUT_PFN: both pillars staged at once, then the PFN over each
+          lv_decorate_half_stage(a, nm, cy, cx, d, st + hi * (16 * LV_PFN_STRIDE), lane, LV_PFN_STRIDE);
+          float* f0 = decorated + row * pfn.units;
+          lv_pfn_warp<9, 2>(st, n0, d.T, pfn_regs, f0, lane);
+          lv_pfn_warp<9, 2>(st + 16 * LV_PFN_STRIDE, n1, d.T, pfn_regs, f0 + pfn.units, lane);
+        }
         continue;
       }
       float4 a0 = z4, b0 = z4, a1 = z4, b1 = z4;
