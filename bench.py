@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--unfused", action="store_true", help="voxelize and decorate as separate stages")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the single-cloud timings of configs[1..3]")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--serial", action="store_true", help="headline from the one-stream loop (no stream pipelining)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -261,6 +262,8 @@ def main():
             ge.build()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from lyft3d_b200.engine import bind_to_gpu_numa_node
+    numa_node = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
@@ -470,7 +473,7 @@ def main():
                             "chain it replaces is pillarize + a PyTorch PFNLayer + scatter (not part of `value`)"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
-                        "d2h_bytes_per_step": pipe.d2h_bytes,
+                        "d2h_bytes_per_step": pipe.d2h_bytes, "rank0_numa_node": numa_node,
                         "note": "HostPipeline: pinned host points -> device -> both paths -> BEV u8 + voxel_num "
                                 "back in pinned host memory every step (copies overlap the next step's kernels); "
                                 "the canvas stays on the device (its consumer is the RPN, voxelnet.py:336)"}}

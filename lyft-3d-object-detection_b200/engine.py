@@ -39,6 +39,36 @@ def apply_env_options(handle):
             handle.set_option(name, int(os.environ[env]) * scale)
 
 
+def bind_to_gpu_numa_node(device):
+    """Pins the calling process to the CPU cores of the NUMA node the GPU hangs off, so that the
+    pinned staging buffers it allocates afterwards (first touch) and the copy threads sit next to
+    the GPU's PCIe root - with one process per GPU and no binding, every rank's host traffic can
+    end up on one socket.  Returns the node, or None when the topology cannot be read (or the
+    cpuset of the container does not intersect the node)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
+        dev_id = getattr(torch.cuda.get_device_properties(device), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev_id)
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 class FrameBatchEngine:
     def __init__(self, device, frames_per_step, points_per_frame,
                  bev_shape=synth.BEV_SHAPE, bev_voxel_size=synth.BEV_VOXEL_SIZE, bev_z_offset=synth.BEV_Z_OFFSET,
