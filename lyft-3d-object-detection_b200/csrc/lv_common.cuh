@@ -162,6 +162,9 @@ __device__ __forceinline__ void lv_mbar_wait(uint64_t* bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void lv_prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ unsigned lv_lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

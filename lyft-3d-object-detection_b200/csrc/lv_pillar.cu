@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(256) pillar_index_kernel(const int32_t* __rest
 
 #define SC_THREADS 256
 #define SC_WARPS (SC_THREADS / 32)
+#define SC_AHEAD 2368  // tiles between a CTA and the one it prefetches for (2 x 148 SMs x 8 CTAs;
+                       // measured 0.937 / 0.935 / 0.945 / 1.018 ms at 1184 / 2368 / 4736 / 9472)
 #define SC_TILE 128   // cells per CTA: every lane owns 4 consecutive cells (one float4 per channel row)
 
 // One CTA = 128 consecutive cells x all C channels of one sample.  No shared memory and at most
@@ -204,7 +206,9 @@ __global__ void __launch_bounds__(256) pillar_index_kernel(const int32_t* __rest
 //     eight warps read the same 512 bytes, so all of them take the same branch below;
 //   - no occupied cell in the tile: one 128-bit zero store per lane and channel row;
 //   - otherwise every lane gathers four features per row - an empty cell reads pillar 0's row,
-//     which stays in L1, and discards it - so the warp never diverges inside the row loop.
+//     which stays in L1, and discards it - so the warp never diverges inside the row loop;
+//   - every feature row is read exactly once, so each CTA also prefetches, into L2, the rows the
+//     CTA SC_AHEAD launches later will gather (0.99 -> 0.935 ms).
 // Warp 0 leaves the map empty for the next call once every warp has read it (the barrier sits
 // in front of the stores and waits for nothing but the index loads).
 template <bool VEC>
@@ -229,6 +233,24 @@ __global__ void __launch_bounds__(SC_THREADS, 8) pillar_canvas_kernel(const floa
     if (j0 + 3 < n_here) occ.w = m[j0 + 3];
   }
   const bool mine = (occ.x & occ.y & occ.z & occ.w) >= 0;   // any of the four >= 0 (sign bit clear)
+  // prefetch for a FUTURE CTA: the last warp reads the indices of the tile SC_AHEAD launches ahead
+  // and pulls the feature rows of its pillars into L2, so that tile's gathers find them there
+  // instead of paying a DRAM round trip per row (every row is read exactly once otherwise)
+  if (VEC && warp == SC_WARPS - 1) {
+    const int64_t ta = (int64_t)blockIdx.x + SC_AHEAD;
+    if (ta < (int64_t)gridDim.x) {
+      const int ba = (int)(ta / tiles_per_sample);
+      const int64_t ca = (ta - (int64_t)ba * tiles_per_sample) * SC_TILE + j0;
+      if (ca + 3 < ncell) {
+        const int4 oa = *reinterpret_cast<const int4*>(map + (int64_t)ba * ncell + ca);
+        const int pa[4] = {oa.x, oa.y, oa.z, oa.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (pa[k] >= 0)
+            for (int c = 0; c < C; c += 32) lv_prefetch_l2(feats + (int64_t)pa[k] * C + c);
+      }
+    }
+  }
   const bool any = __syncthreads_or(mine);
   if (any && warp == 0 && mine) {
     if (occ.x >= 0) m[j0] = -1;
