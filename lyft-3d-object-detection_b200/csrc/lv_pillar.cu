@@ -233,6 +233,14 @@ __global__ void __launch_bounds__(SC_THREADS, 8) pillar_canvas_kernel(const floa
     if (j0 + 3 < n_here) occ.w = m[j0 + 3];
   }
   const bool mine = (occ.x & occ.y & occ.z & occ.w) >= 0;   // any of the four >= 0 (sign bit clear)
+  const bool any = __syncthreads_or(mine);
+  if (any && warp == 0 && mine) {
+    if (occ.x >= 0) m[j0] = -1;
+    if (occ.y >= 0) m[j0 + 1] = -1;
+    if (occ.z >= 0) m[j0 + 2] = -1;
+    if (occ.w >= 0) m[j0 + 3] = -1;
+  }
+  // (behind the barrier, so that only this warp's own rows wait for the extra index load)
   // prefetch for a FUTURE CTA: the last warp reads the indices of the tile SC_AHEAD launches ahead
   // and pulls the feature rows of its pillars into L2, so that tile's gathers find them there
   // instead of paying a DRAM round trip per row (every row is read exactly once otherwise)
@@ -250,13 +258,6 @@ __global__ void __launch_bounds__(SC_THREADS, 8) pillar_canvas_kernel(const floa
             for (int c = 0; c < C; c += 32) lv_prefetch_l2(feats + (int64_t)pa[k] * C + c);
       }
     }
-  }
-  const bool any = __syncthreads_or(mine);
-  if (any && warp == 0 && mine) {
-    if (occ.x >= 0) m[j0] = -1;
-    if (occ.y >= 0) m[j0 + 1] = -1;
-    if (occ.z >= 0) m[j0 + 2] = -1;
-    if (occ.w >= 0) m[j0 + 3] = -1;
   }
   float* row = canvas + ((int64_t)b * C + warp) * ncell + cell0 + j0;
   const int64_t row_step = (int64_t)SC_WARPS * ncell;
