@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
   const int NV = 1 << p.low_bits;
   int* slot_tab = smem;                    // [NV][T]
   int* total = slot_tab + NV * p.T;        // [NV]
-  int* wcnt = total + NV;                  // [8][NV]
+  int* s_cell = total + NV;                // [NV] creator cell of every voxel of the bin
+  int* wcnt = s_cell + NV;                 // [8][NV]
   float* stage = reinterpret_cast<float*>(wcnt + VX_WARPS * NV);  // [8][T*C_out] (DECO only)
   __shared__ long long s_row0;
 
@@ -507,14 +508,14 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
   const uint32_t* keys = p.keys + (fstart - p.pt_lo);
   const int32_t* vals = p.vals + (fstart - p.pt_lo);
 
-  for (int i = threadIdx.x; i < NV; i += VX_THREADS) total[i] = 0;
+  for (int i = threadIdx.x; i < NV; i += VX_THREADS) {
+    total[i] = 0;
+    s_cell[i] = i < nv ? p.creator_cell[(fstart - p.pt_lo) + v0 + i] : 0;   // in flight during phase 1
+  }
   const unsigned lt = lv_lanemask_lt();
   const unsigned lowmask = NV - 1;
   // ---- phase 1: stable rank by voxel inside the bin, tile by tile (2048 points) ----
   for (int tile0 = seg_lo; tile0 < seg_hi; tile0 += VX_CHUNK) {
-    for (int i = threadIdx.x; i < VX_WARPS * NV; i += VX_THREADS) wcnt[i] = 0;
-    __syncthreads();
-    int* mycnt = wcnt + warp * NV;
     unsigned dig[VX_ITEMS];
     int val[VX_ITEMS], rnk[VX_ITEMS];
     // every warp owns a contiguous span of the tile (point order = warp, round, lane); the
@@ -525,17 +526,21 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
     const int rounds = span >> 5;
     const int base = tile0 + warp * span;
     const int tile_hi = tile0 + n_tile;
+    // the tile's keys and values: all loads in flight while the counters are reset
 #pragma unroll
     for (int r = 0; r < VX_ITEMS; ++r) {
-      dig[r] = 0xffffffffu;
-      val[r] = 0;
+      const int pos = base + r * 32 + lane;
+      const bool in = r < rounds && pos < tile_hi;
+      dig[r] = in ? (keys[pos] & lowmask) : 0xffffffffu;
+      val[r] = in ? vals[pos] : 0;
+    }
+    for (int i = threadIdx.x; i < VX_WARPS * NV; i += VX_THREADS) wcnt[i] = 0;
+    __syncthreads();
+    int* mycnt = wcnt + warp * NV;
+#pragma unroll
+    for (int r = 0; r < VX_ITEMS; ++r) {
       rnk[r] = 0;
       if (r >= rounds) continue;  // warp-uniform
-      const int pos = base + r * 32 + lane;
-      if (pos < tile_hi) {
-        dig[r] = keys[pos] & lowmask;
-        val[r] = vals[pos];
-      }
       const unsigned peers = __match_any_sync(0xffffffffu, dig[r]);
       const int leader = __ffs(peers) - 1;
       int old = 0;
@@ -571,7 +576,6 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
   __syncthreads();
   // ---- phase 2: the output rows of the bin (contiguous in memory) ----
   const long long row0 = s_row0;
-  const int32_t* ccell = p.creator_cell + (fstart - p.pt_lo);
   if (row0 + v0 + nv > p.capacity) nv = (int)(p.capacity - (row0 + v0) > 0 ? p.capacity - (row0 + v0) : 0);
   if (MODE == VX_OUT_MEAN) {
     // one thread per voxel: mean of its stored points (the padded slots add zeros), count, coordinates.
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
       if (n > p.T) n = p.T;
       const long long row = row0 + v0 + v;
       int cx, cy, cz;
-      vx_cell_coords(p, ccell[v0 + v], cz, cy, cx);
+      vx_cell_coords(p, s_cell[v], cz, cy, cx);
       p.num_points[row] = n;
       if (p.coord_cols == 4) {
         *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(f, cz, cy, cx);  // preprocess.py:44-50
@@ -612,7 +616,7 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
       total[v] = n;
       const long long row = row0 + v0 + v;
       int cx, cy, cz;
-      vx_cell_coords(p, ccell[v0 + v], cz, cy, cx);
+      vx_cell_coords(p, s_cell[v], cz, cy, cx);
       p.num_points[row] = n;
       if (p.coord_cols == 4) {
         *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(f, cz, cy, cx);  // preprocess.py:44-50
@@ -661,7 +665,7 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
         const int nm = hi ? n1 : n0;
         float4 a = z4;
         if (sub < nm) a = __ldg(pts4 + sl[hi * p.T + sub]);
-        const int cm = ccell[v0 + v + hi];
+        const int cm = s_cell[v + hi];
         float* dst0 = decorated + row * per;
         if (MODE == VX_OUT_DECORATE) {
           lv_decorate_zero_tail(n0, d, dst0, lane);
@@ -688,7 +692,7 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
       if (lane + 32 < n0) b0 = __ldg(pts4 + sl[lane + 32]);
       if (lane < n1) a1 = __ldg(pts4 + sl[p.T + lane]);
       if (lane + 32 < n1) b1 = __ldg(pts4 + sl[p.T + lane + 32]);
-      const int c0 = ccell[v0 + v], c1 = two ? ccell[v0 + v + 1] : 0;
+      const int c0 = s_cell[v], c1 = two ? s_cell[v + 1] : 0;
       float* dst0 = decorated + row * per;
       if (MODE == VX_OUT_DECORATE) {
         lv_decorate_zero_tail(n0, d, dst0, lane);
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
       if (sub == 0) {
         p.num_points[row] = n;
         int cx, cy, cz;
-        vx_cell_coords(p, ccell[v0 + v], cz, cy, cx);
+        vx_cell_coords(p, s_cell[v], cz, cy, cx);
         if (p.coord_cols == 4) {
           *reinterpret_cast<int4*>(p.coords + row * 4) = make_int4(f, cz, cy, cx);
         } else {
@@ -877,7 +881,7 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   const int NV = 1 << L;
   const size_t deco_stage = pfn ? (size_t)VX_WARPS * T * LV_PFN_STRIDE * 4
                                  : (deco ? (size_t)VX_WARPS * (T * deco->C_out + 4) * 4 : 0);
-  const size_t smem_bins = ((size_t)NV * T + NV + (size_t)VX_WARPS * NV) * 4 + deco_stage;
+  const size_t smem_bins = ((size_t)NV * T + 2 * NV + (size_t)VX_WARPS * NV) * 4 + deco_stage;
   LV_REQUIRE(smem_bins <= 220 * 1024, "lv_voxelize: max_points %d x max_voxels %d needs %zu bytes of shared memory "
              "per bin (limit 220 KB)", T, V, smem_bins);
   LV_REQUIRE((int64_t)NV * T < (1ll << 20), "lv_voxelize: bin of %d voxels x %d points is too large", NV, T);
