@@ -236,6 +236,44 @@ int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const float* h_po
                      int32_t n_frames, const int64_t* h_frame_offsets, float* h_voxels,
                      int32_t* h_coords, int32_t* h_num_points, int32_t* h_voxel_num);
 
+/* Block-filtering variant: VoxelGeneratorV2(block_filtering=True, block_factor, block_size,
+ * height_threshold) - kwargs at second/second/builder/voxel_builder.py:28-31, fields of
+ * second/second/protos/voxel_generator.proto:10-13, used by
+ * second/second/configs/nuscenes/all.fhd.config:9-12.  PARITY UNPINNED: the rule lives in spconv 1.x
+ * (points_to_voxel_3d_with_filtering, source not in the reference tree); restated in
+ * oracle/voxel_oracle.c: every stored point updates the z-min/z-max of its
+ * (y / block_factor, x / block_factor) block; a voxel survives iff, over the block_size x block_size
+ * window of blocks around its own, height = max - min satisfies
+ * height > height_threshold && height < height_high_threshold (+inf: the rule before spconv 1.2);
+ * survivors keep their first-come order.  The xy grid must be divisible by block_factor. */
+typedef struct lv_block_filter {
+  int32_t block_factor;
+  int32_t block_size;
+  float height_threshold;
+  float height_high_threshold;
+} lv_block_filter;
+
+/* The filter alone, on padded per-frame voxelizer output (layouts of lv_voxelize).  Outputs must not
+ * alias the inputs.  d_out_voxel_num (n_frames) = survivors per frame; rows beyond it are zero-filled
+ * iff cfg->zero_tail.  d_out_mask (optional, (n_frames, V) int32) = keep flag of every unfiltered voxel. */
+int lv_voxel_block_filter(lv_handle* h, const lv_voxel_config* cfg, const lv_block_filter* flt,
+                          int32_t n_frames, const float* d_voxels, const int32_t* d_coords,
+                          const int32_t* d_num_points, const int32_t* d_voxel_num, float* d_out_voxels,
+                          int32_t* d_out_coords, int32_t* d_out_num_points, int32_t* d_out_voxel_num,
+                          int32_t* d_out_mask, lv_stream stream);
+
+/* lv_voxelize (overflow_mode must be LV_OVERFLOW_CONTINUE) followed by the filter; the unfiltered
+ * voxels live in the handle's workspace. */
+int lv_voxelize_filtered(lv_handle* h, const lv_voxel_config* cfg, const lv_block_filter* flt,
+                         const float* d_points, int32_t n_frames, const int64_t* h_frame_offsets,
+                         float* d_voxels, int32_t* d_coords, int32_t* d_num_points,
+                         int32_t* d_voxel_num, int32_t* d_mask, lv_stream stream);
+
+int lv_voxelize_filtered_host(lv_handle* h, const lv_voxel_config* cfg, const lv_block_filter* flt,
+                              const float* h_points, int32_t n_frames, const int64_t* h_frame_offsets,
+                              float* h_voxels, int32_t* h_coords, int32_t* h_num_points,
+                              int32_t* h_voxel_num);
+
 /* ------------------------------------------------------------------ PointPillars
  *
  * lv_pillar_decorate replaces the decoration part of

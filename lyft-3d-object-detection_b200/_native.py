@@ -45,6 +45,14 @@ class VoxelConfig(ctypes.Structure):
                 ("zero_tail", ctypes.c_int32)]
 
 
+class BlockFilter(ctypes.Structure):
+    """struct lv_block_filter."""
+    _fields_ = [("block_factor", ctypes.c_int32),
+                ("block_size", ctypes.c_int32),
+                ("height_threshold", ctypes.c_float),
+                ("height_high_threshold", ctypes.c_float)]
+
+
 _vp = ctypes.c_void_p
 _i32 = ctypes.c_int32
 _i64 = ctypes.c_int64
@@ -81,6 +89,12 @@ SIGNATURES = {
                                                _vp, _vp, _vp, _vp]),
     "lv_unpad_batch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "lv_voxelize_host": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "lv_voxel_block_filter": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), ctypes.POINTER(BlockFilter), _i32, _vp,
+                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lv_voxelize_filtered": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), ctypes.POINTER(BlockFilter), _vp, _i32,
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lv_voxelize_filtered_host": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), ctypes.POINTER(BlockFilter), _vp,
+                                                 _i32, _vp, _vp, _vp, _vp, _vp]),
     "lv_pillar_out_channels": (ctypes.c_int, [_i32, _i32, _i32]),
     "lv_pillar_decorate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32,
                                           _i32, _i32, _vp, _vp]),

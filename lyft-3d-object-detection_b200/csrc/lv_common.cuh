@@ -87,6 +87,7 @@ struct lv_handle {
   lv_buffer vox_row_base;
   lv_mirror vox_frame_offsets, vox_chunk_table, vox_chunk_frame;
   lv_buffer vox_stage_points, vox_stage_out[4];
+  lv_buffer flt_ranges, flt_dst, flt_tmp[4];   // block filter: z ranges per block, destination rows, unfiltered voxels
 
   // pillar
   lv_buffer pil_map;                  // i32 [B][ny*nx]
@@ -102,7 +103,8 @@ inline std::vector<lv_buffer*> lv_all_buffers(lv_handle* h) {
           &h->bev_stage_map, &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1], &h->vox_vals[0],
           &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state, &h->vox_row_base,
           &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_chunk_frame.dev, &h->vox_stage_points, &h->vox_stage_out[0],
-          &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3], &h->pil_map, &h->ing_offsets.dev,
+          &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3], &h->flt_ranges, &h->flt_dst, &h->flt_tmp[0], &h->flt_tmp[1],
+          &h->flt_tmp[2], &h->flt_tmp[3], &h->pil_map, &h->ing_offsets.dev,
           &h->ing_tm.dev, &h->ing_lag.dev, &h->ing_has.dev};
 }
 

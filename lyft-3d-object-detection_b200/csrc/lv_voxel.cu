@@ -1092,9 +1092,9 @@ extern "C" int lv_pillarize_pfn_concat(lv_handle* h, const lv_voxel_config* cfg,
                 capacity_rows, d_voxel_offsets, &d, d_features, &c, stream);
 }
 
-extern "C" int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const float* h_points, int32_t n_frames,
-                                const int64_t* h_frame_offsets, float* h_voxels, int32_t* h_coords,
-                                int32_t* h_num_points, int32_t* h_voxel_num) {
+static int vx_host_run(lv_handle* h, const lv_voxel_config* cfg, const lv_block_filter* flt, const float* h_points,
+                       int32_t n_frames, const int64_t* h_frame_offsets, float* h_voxels, int32_t* h_coords,
+                       int32_t* h_num_points, int32_t* h_voxel_num) {
   LV_REQUIRE(h != nullptr, "lv_voxelize_host: null handle");
   LV_REQUIRE(cfg && h_frame_offsets && n_frames >= 0, "lv_voxelize_host: bad arguments");
   LV_REQUIRE(cfg->num_features >= 3 && cfg->max_points > 0 && cfg->max_voxels > 0, "lv_voxelize_host: bad config");
@@ -1111,9 +1111,14 @@ extern "C" int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const 
   LV_CHECK(h->vox_stage_out[2].ensure(F * V * 4, st));
   LV_CHECK(h->vox_stage_out[3].ensure(F * 4, st));
   if (pt_bytes) LV_CHECK_CUDA(cudaMemcpyAsync(h->vox_stage_points.ptr, h_points, pt_bytes, cudaMemcpyHostToDevice, st));
-  LV_CHECK(lv_voxelize(h, cfg, h->vox_stage_points.as<float>(), n_frames, h_frame_offsets, h->vox_stage_out[0].as<float>(),
-                       h->vox_stage_out[1].as<int32_t>(), h->vox_stage_out[2].as<int32_t>(),
-                       h->vox_stage_out[3].as<int32_t>(), st));
+  if (flt)
+    LV_CHECK(lv_voxelize_filtered(h, cfg, flt, h->vox_stage_points.as<float>(), n_frames, h_frame_offsets,
+                                  h->vox_stage_out[0].as<float>(), h->vox_stage_out[1].as<int32_t>(),
+                                  h->vox_stage_out[2].as<int32_t>(), h->vox_stage_out[3].as<int32_t>(), nullptr, st));
+  else
+    LV_CHECK(lv_voxelize(h, cfg, h->vox_stage_points.as<float>(), n_frames, h_frame_offsets, h->vox_stage_out[0].as<float>(),
+                         h->vox_stage_out[1].as<int32_t>(), h->vox_stage_out[2].as<int32_t>(),
+                         h->vox_stage_out[3].as<int32_t>(), st));
   // voxel_num first: with zero_tail == 0 only the live rows are brought back
   LV_CHECK_CUDA(cudaMemcpyAsync(h_voxel_num, h->vox_stage_out[3].ptr, F * 4, cudaMemcpyDeviceToHost, st));
   LV_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -1129,6 +1134,20 @@ extern "C" int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const 
   }
   LV_CHECK_CUDA(cudaStreamSynchronize(st));
   return LV_OK;
+}
+
+extern "C" int lv_voxelize_host(lv_handle* h, const lv_voxel_config* cfg, const float* h_points, int32_t n_frames,
+                                const int64_t* h_frame_offsets, float* h_voxels, int32_t* h_coords,
+                                int32_t* h_num_points, int32_t* h_voxel_num) {
+  return vx_host_run(h, cfg, nullptr, h_points, n_frames, h_frame_offsets, h_voxels, h_coords, h_num_points, h_voxel_num);
+}
+
+extern "C" int lv_voxelize_filtered_host(lv_handle* h, const lv_voxel_config* cfg, const lv_block_filter* flt,
+                                         const float* h_points, int32_t n_frames, const int64_t* h_frame_offsets,
+                                         float* h_voxels, int32_t* h_coords, int32_t* h_num_points,
+                                         int32_t* h_voxel_num) {
+  LV_REQUIRE(flt != nullptr, "lv_voxelize_filtered_host: null filter");
+  return vx_host_run(h, cfg, flt, h_points, n_frames, h_frame_offsets, h_voxels, h_coords, h_num_points, h_voxel_num);
 }
 
 extern "C" int lv_unpad_batch(lv_handle* h, const float* d_voxels, const int32_t* d_num_points, const int32_t* d_coors,

@@ -41,14 +41,27 @@ def _make_config(voxel_size, coors_range, max_points, max_voxels, num_features, 
     return cfg
 
 
+def _make_filter(block_filter):
+    """(block_factor, block_size, height_threshold, height_high_threshold | None) -> struct lv_block_filter."""
+    bf, bs, lo, hi = block_filter
+    flt = nat.BlockFilter()
+    flt.block_factor = int(bf)
+    flt.block_size = int(bs)
+    flt.height_threshold = float(lo)
+    flt.height_high_threshold = float("inf") if hi is None else float(hi)
+    return flt
+
+
 def voxelize_frames(points, frame_offsets, voxel_size, coors_range, max_points, max_voxels,
-                    overflow="continue", zero_tail=True, handle=None):
+                    overflow="continue", zero_tail=True, handle=None, block_filter=None):
     """Batched voxelization of F independent clouds.
 
     points (N_total, C) float32 rows (numpy or CUDA tensor); frame_offsets int64 (F+1).
     Returns padded per-frame arrays: voxels (F,V,T,C), coordinates (F,V,3) zyx,
     num_points_per_voxel (F,V), voxel_num (F).  With zero_tail=False rows at and
-    beyond voxel_num[f] are unspecified.
+    beyond voxel_num[f] are unspecified.  block_filter = (block_factor, block_size,
+    height_threshold, height_high_threshold) runs the spconv block-filtering variant
+    (lv_voxelize_filtered; `continue` overflow rule only).
     """
     if overflow not in ("continue", "break"):
         raise ValueError("overflow must be 'continue' or 'break'")
@@ -70,9 +83,16 @@ def voxelize_frames(points, frame_offsets, voxel_size, coors_range, max_points, 
         vnum = torch.empty((F,), dtype=torch.int32, device=dev)
         h = handle or nat.get_handle(dev.index)
         with torch.cuda.device(dev):
-            nat.check(lib.lv_voxelize(h.ptr, ctypes.byref(cfg), pts.data_ptr(), F, offs.ctypes.data,
-                                      voxels.data_ptr(), coords.data_ptr(), num.data_ptr(), vnum.data_ptr(),
-                                      nat.current_stream_ptr(dev)))
+            if block_filter is not None:
+                flt = _make_filter(block_filter)
+                nat.check(lib.lv_voxelize_filtered(h.ptr, ctypes.byref(cfg), ctypes.byref(flt), pts.data_ptr(), F,
+                                                   offs.ctypes.data, voxels.data_ptr(), coords.data_ptr(),
+                                                   num.data_ptr(), vnum.data_ptr(), None,
+                                                   nat.current_stream_ptr(dev)))
+            else:
+                nat.check(lib.lv_voxelize(h.ptr, ctypes.byref(cfg), pts.data_ptr(), F, offs.ctypes.data,
+                                          voxels.data_ptr(), coords.data_ptr(), num.data_ptr(), vnum.data_ptr(),
+                                          nat.current_stream_ptr(dev)))
         return voxels, coords, num, vnum
     pts = np.ascontiguousarray(points, dtype=np.float32)
     if pts.ndim != 2:
@@ -85,8 +105,14 @@ def voxelize_frames(points, frame_offsets, voxel_size, coors_range, max_points, 
     num = alloc((F, V), dtype=np.int32)
     vnum = np.zeros((F,), dtype=np.int32)
     h = handle or nat.get_handle()
-    nat.check(lib.lv_voxelize_host(h.ptr, ctypes.byref(cfg), pts.ctypes.data, F, offs.ctypes.data,
-                                   voxels.ctypes.data, coords.ctypes.data, num.ctypes.data, vnum.ctypes.data))
+    if block_filter is not None:
+        flt = _make_filter(block_filter)
+        nat.check(lib.lv_voxelize_filtered_host(h.ptr, ctypes.byref(cfg), ctypes.byref(flt), pts.ctypes.data, F,
+                                                offs.ctypes.data, voxels.ctypes.data, coords.ctypes.data,
+                                                num.ctypes.data, vnum.ctypes.data))
+    else:
+        nat.check(lib.lv_voxelize_host(h.ptr, ctypes.byref(cfg), pts.ctypes.data, F, offs.ctypes.data,
+                                       voxels.ctypes.data, coords.ctypes.data, num.ctypes.data, vnum.ctypes.data))
     return voxels, coords, num, vnum
 
 
@@ -97,8 +123,6 @@ class VoxelGeneratorV2:
                  block_filtering=False, block_factor=8, block_size=3, height_threshold=0.1,
                  height_high_threshold=2.0, overflow="continue"):
         assert full_mean is False, "full_mean is not supported (spconv asserts the same)"
-        if block_filtering:
-            raise NotImplementedError("block_filtering voxelization is out of the first scope (SURVEY.md 8f n4)")
         if overflow not in ("continue", "break"):
             raise ValueError("overflow must be 'continue' or 'break'")
         point_cloud_range = np.array(point_cloud_range, dtype=np.float32)
@@ -112,6 +136,16 @@ class VoxelGeneratorV2:
         self._grid_size = grid_size
         self._full_mean = full_mean
         self._overflow = overflow
+        # block filtering (voxel_builder.py:28-31; all.fhd.config:9-12).  The rule is spconv's
+        # (PARITY UNPINNED, see include/lyft_voxel.h); spconv asserts the same divisibility.
+        self._block_filter = None
+        if block_filtering:
+            if overflow != "continue":
+                raise ValueError("block_filtering exists only with the 'continue' overflow rule")
+            assert block_size > 0
+            assert grid_size[0] % block_factor == 0
+            assert grid_size[1] % block_factor == 0
+            self._block_filter = (int(block_factor), int(block_size), float(height_threshold), height_high_threshold)
 
     # -- the V2 dict API (preprocess.py:305-317, inference.py:68-69)
     def _run(self, points, max_voxels, padded):
@@ -119,7 +153,8 @@ class VoxelGeneratorV2:
         n = points.shape[0]
         voxels, coords, num, vnum = voxelize_frames(
             points, np.array([0, n], dtype=np.int64), self._voxel_size, self._point_cloud_range,
-            self._max_num_points, mv, overflow=self._overflow, zero_tail=padded)
+            self._max_num_points, mv, overflow=self._overflow, zero_tail=padded,
+            block_filter=self._block_filter)
         k = int(vnum[0])
         return voxels[0], coords[0], num[0], k
 

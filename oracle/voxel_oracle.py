@@ -49,6 +49,12 @@ def _load():
             ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.lvo_points_to_voxel_filtered.restype = ctypes.c_int32
+        lib.lvo_points_to_voxel_filtered.argtypes = [
+            ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float,
+            ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         lib.lvo_grid_size.restype = None
         lib.lvo_grid_size.argtypes = [ctypes.c_void_p] * 3
         lib.lvo_bev_counts.restype = None
@@ -149,6 +155,65 @@ def points_to_voxel(points, voxel_size, coors_range, max_points, max_voxels,
     """One-shot C oracle -> (voxels, coordinates, num_points_per_voxel)."""
     return VoxelOracle(voxel_size, coors_range, max_points, max_voxels).generate(
         points, overflow=overflow)
+
+
+def points_to_voxel_filtered(points, voxel_size, coors_range, max_points, max_voxels, block_factor=8,
+                             block_size=3, height_threshold=0.1, height_high_threshold=2.0):
+    """Block-filtering voxelizer, C oracle (lvo_points_to_voxel_filtered) + the compaction spconv does
+    in Python (`coors[voxel_mask]`).  PARITY UNPINNED (spconv 1.x, source absent; see voxel_oracle.c).
+    height_high_threshold=None -> +inf (the rule before spconv 1.2).
+    Returns (voxels, coordinates, num_points_per_voxel, voxel_mask) - the first three filtered, the
+    mask over the unfiltered voxels."""
+    lib = _load()
+    points = np.ascontiguousarray(points, dtype=np.float32)
+    voxel_size = np.asarray(voxel_size, dtype=np.float32).copy()
+    coors_range = np.asarray(coors_range, dtype=np.float32).copy()
+    gs = grid_size(voxel_size, coors_range)
+    assert gs[0] % block_factor == 0 and gs[1] % block_factor == 0 and block_size > 0
+    n, c = points.shape
+    cmap = -np.ones(int(np.prod(gs.astype(np.int64))), dtype=np.int32)
+    voxels = np.zeros((max_voxels, max_points, c), dtype=np.float32)
+    coors = np.zeros((max_voxels, 3), dtype=np.int32)
+    num = np.zeros((max_voxels,), dtype=np.int32)
+    mask = np.zeros((max_voxels,), dtype=np.int32)
+    nb = int(gs[1] // block_factor) * int(gs[0] // block_factor)
+    mins = np.empty(nb, dtype=np.float32)
+    maxs = np.empty(nb, dtype=np.float32)
+    hi = np.inf if height_high_threshold is None else height_high_threshold
+    vn = lib.lvo_points_to_voxel_filtered(
+        points.ctypes.data, n, c, voxel_size.ctypes.data, coors_range.ctypes.data, max_points,
+        max_voxels, block_factor, block_size, ctypes.c_float(height_threshold), ctypes.c_float(hi),
+        cmap.ctypes.data, voxels.ctypes.data, coors.ctypes.data, num.ctypes.data, mask.ctypes.data,
+        mins.ctypes.data, maxs.ctypes.data)
+    keep = mask[:vn].astype(bool)
+    return voxels[:vn][keep], coors[:vn][keep], num[:vn][keep], keep
+
+
+def block_filter_numpy(voxels, coors, num, grid_xyz, block_factor, block_size, height_threshold,
+                       height_high_threshold=2.0):
+    """Independent numpy statement of the block filter on voxelizer OUTPUTS (the stored points of a
+    voxel are exactly the points that updated its block's z range): returns the keep mask."""
+    voxels = np.asarray(voxels, dtype=np.float32)
+    V, T, _ = voxels.shape
+    BH, BW = int(grid_xyz[1]) // block_factor, int(grid_xyz[0]) // block_factor
+    mins = np.full((BH, BW), 99999999, dtype=np.float32)
+    maxs = np.full((BH, BW), -99999999, dtype=np.float32)
+    live = np.arange(T)[None, :] < np.asarray(num)[:, None]
+    z = voxels[:, :, 2]
+    by = np.asarray(coors)[:, 1] // block_factor
+    bx = np.asarray(coors)[:, 2] // block_factor
+    zmin = np.where(live, z, np.float32(np.inf)).min(axis=1) if V else np.zeros(0, np.float32)
+    zmax = np.where(live, z, np.float32(-np.inf)).max(axis=1) if V else np.zeros(0, np.float32)
+    np.minimum.at(mins, (by, bx), zmin.astype(np.float32))
+    np.maximum.at(maxs, (by, bx), zmax.astype(np.float32))
+    keep = np.zeros(V, dtype=bool)
+    hi = np.float32(np.inf) if height_high_threshold is None else np.float32(height_high_threshold)
+    for i in range(V):
+        y0, y1 = max(0, by[i] - block_size // 2), min(BH, by[i] + block_size - block_size // 2)
+        x0, x1 = max(0, bx[i] - block_size // 2), min(BW, bx[i] + block_size - block_size // 2)
+        h = np.float32(maxs[y0:y1, x0:x1].max() - mins[y0:y1, x0:x1].min())
+        keep[i] = (h > np.float32(height_threshold)) and (h < hi)
+    return keep
 
 
 def bev_counts_c(points_nx, shape, voxel_size, z_offset):

@@ -162,8 +162,6 @@ def test_edges_and_errors(vg, vo):
     r = gen.generate(same, 100)
     assert r["num_points_per_voxel"].tolist() == [5] and r["voxels"][0, :, 3].tolist() == [0, 1, 2, 3, 4]
     with pytest.raises(Exception):
-        vg.VoxelGeneratorV2(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 5, block_filtering=True)
-    with pytest.raises(Exception):
         vg.VoxelGeneratorV2((0.001, 0.001, 0.001), synth.PILLAR_RANGE, 5).generate(pts, 10)   # grid > 2^28 cells
 
 
