@@ -116,6 +116,25 @@ int lv_bev_rasterize_host(lv_handle* h, const float* h_points, int32_t point_str
                           float max_intensity, float* h_raw, float* h_norm, uint8_t* h_u8,
                           const uint8_t* h_map_u8, float* h_chw);
 
+/* Target rasterisation: draw_boxes of generating-dataset/generating_train_bev.py:127-139, the
+ * class-index image written to "{token}_target.png" (:214-223).  Frame f paints boxes
+ * [h_box_offsets[f], h_box_offsets[f+1]) in that order, later boxes over earlier ones:
+ *   d_corners  float64 (n_boxes, 3, 4)  Box.bottom_corners() in car space (rows x, y, z; the four
+ *                                       bottom corners in order around the footprint)
+ *   d_colors   int32   (n_boxes)        classes.index(box.name) + 1  (1..255)
+ *   d_target   uint8   (n_frames, shape[0], shape[1])  target[:, :, 0]; 0 = background.  Every byte
+ *                                       is written.
+ * Corners go through car_to_voxel_coords (:73-82; fp64) and np.int0 (C truncation);
+ * the filled polygon is cv2.drawContours(..., -1): OpenCV's Line + scanline fill rule, restated
+ * in oracle/draw_oracle.py and pinned against cv2 4.13.  Vertices are clamped to +-2^20 pixels. */
+int lv_draw_boxes(lv_handle* h, const double* d_corners, const int32_t* d_colors, int32_t n_frames,
+                  const int64_t* h_box_offsets, const int32_t shape[3], const double voxel_size[3],
+                  double z_offset, uint8_t* d_target, lv_stream stream);
+
+int lv_draw_boxes_host(lv_handle* h, const double* h_corners, const int32_t* h_colors,
+                       int32_t n_frames, const int64_t* h_box_offsets, const int32_t shape[3],
+                       const double voxel_size[3], double z_offset, uint8_t* h_target);
+
 /* normalize_voxel_intensities alone (generating_train_bev.py:103-104) on a
  * device array of n float32: out = clip(in / max_intensity, 0, 1). */
 int lv_bev_normalize(lv_handle* h, const float* d_in, int64_t n, float max_intensity,

@@ -225,3 +225,56 @@ def quantize_u8(points, shape, voxel_size=(0.5, 0.5, 1), z_offset=0, max_intensi
     res = rasterize_frames(rows, np.array([0, rows.shape[0]], dtype=np.int64), shape, voxel_size, z_offset,
                            max_intensity, want=("u8",))
     return res["u8"][0]
+
+
+def rasterize_targets(corners, colors, box_offsets, shape, voxel_size, z_offset=0.0, handle=None):
+    """Batched target rasterisation (lv_draw_boxes): frame f paints boxes
+    [box_offsets[f], box_offsets[f+1]) in order, later over earlier.
+
+    corners (n_boxes, 3, 4) float64 car-space Box.bottom_corners(), colors (n_boxes,) int32
+    (classes.index(name) + 1); numpy or CUDA tensors.  Returns uint8 (F, shape[0], shape[1]) =
+    ``target[:, :, 0]`` of generating_train_bev.py:214-221 per frame (same kind as the input)."""
+    import ctypes
+    lib = nat.load()
+    offs = np.ascontiguousarray(box_offsets, dtype=np.int64)
+    F = offs.shape[0] - 1
+    shp = (ctypes.c_int32 * 3)(*_shape3(shape))
+    vs = (ctypes.c_double * 3)(*_vs3(voxel_size))
+    H, W = int(shape[0]), int(shape[1])
+    if _is_cuda_tensor(corners):
+        import torch
+        c = corners.contiguous()
+        k = colors.contiguous()
+        if c.dtype != torch.float64 or k.dtype != torch.int32 or tuple(c.shape[1:]) != (3, 4):
+            raise Exception("corners must be (n, 3, 4) float64 and colors (n,) int32")
+        out = torch.empty((F, H, W), dtype=torch.uint8, device=c.device)
+        h = handle or nat.get_handle(c.device.index)
+        with torch.cuda.device(c.device):
+            nat.check(lib.lv_draw_boxes(h.ptr, c.data_ptr(), k.data_ptr(), F, offs.ctypes.data, shp, vs,
+                                        float(z_offset), out.data_ptr(), nat.current_stream_ptr(c.device)))
+        return out
+    c = np.ascontiguousarray(corners, dtype=np.float64).reshape(-1, 3, 4)
+    k = np.ascontiguousarray(colors, dtype=np.int32)
+    if c.shape[0] != k.shape[0] or (F > 0 and offs[-1] != c.shape[0]):
+        raise Exception("corners, colors and box_offsets disagree")
+    out = np.empty((F, H, W), dtype=np.uint8)
+    h = handle or nat.get_handle()
+    nat.check(lib.lv_draw_boxes_host(h.ptr, c.ctypes.data, k.ctypes.data, F, offs.ctypes.data, shp, vs,
+                                     float(z_offset), out.ctypes.data))
+    return out
+
+
+def draw_boxes(im, voxel_size, boxes, classes, z_offset=0.0):
+    """generating_train_bev.py:127-139, same signature and side effect: paints every box's bottom
+    footprint into `im` (H, W, 3) in place with the value classes.index(box.name) + 1.  `boxes` are
+    devkit Box objects (anything with ``bottom_corners()`` -> (3, 4) and ``name``).  An unknown class
+    name raises, as ``classes.index`` does in the reference."""
+    boxes = list(boxes)
+    if not boxes:
+        return
+    colors = np.array([classes.index(b.name) + 1 for b in boxes], dtype=np.int32)
+    corners = np.stack([np.asarray(b.bottom_corners(), dtype=np.float64) for b in boxes])
+    target = rasterize_targets(corners, colors, np.array([0, len(boxes)], dtype=np.int64), im.shape, voxel_size,
+                               z_offset)[0]
+    painted = target > 0
+    im[painted] = target[painted].astype(im.dtype)[:, None]

@@ -80,6 +80,8 @@ struct lv_handle {
   lv_buffer bev_dirty;                // 1 bit per 4 counts, kept all-zero between calls
   lv_mirror bev_seg_offsets, bev_seg_frame, bev_seg_tm;
   lv_buffer bev_stage_points, bev_stage_out[5], bev_stage_map;  // *_host staging
+  lv_mirror draw_offsets;             // target rasterisation: box offsets per frame
+  lv_buffer draw_recs, draw_stage[3]; // per-box line / scanline-edge records; *_host staging
 
   // voxelizer
   lv_buffer vox_map;                  // i32 [frames_in_flight][grid cells], kept all-INT_MAX between calls
@@ -100,7 +102,8 @@ struct lv_handle {
 inline std::vector<lv_buffer*> lv_all_buffers(lv_handle* h) {
   return {&h->bev_counts, &h->bev_dirty, &h->bev_seg_offsets.dev, &h->bev_seg_frame.dev, &h->bev_seg_tm.dev, &h->bev_stage_points,
           &h->bev_stage_out[0], &h->bev_stage_out[1], &h->bev_stage_out[2], &h->bev_stage_out[3], &h->bev_stage_out[4],
-          &h->bev_stage_map, &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1], &h->vox_vals[0],
+          &h->bev_stage_map, &h->draw_offsets.dev, &h->draw_recs, &h->draw_stage[0], &h->draw_stage[1], &h->draw_stage[2],
+          &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1], &h->vox_vals[0],
           &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state, &h->vox_row_base,
           &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_chunk_frame.dev, &h->vox_stage_points, &h->vox_stage_out[0],
           &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3], &h->flt_ranges, &h->flt_dst, &h->flt_tmp[0], &h->flt_tmp[1],

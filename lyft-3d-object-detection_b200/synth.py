@@ -145,3 +145,31 @@ def ingest_case(n_sweeps=4, n_key=6000, seed=77):
                        "timestamp": ts_us - 50_000 * (s + 1)})
         at += m
     return key, sweeps, ts_us
+
+
+# Lyft classes (generating-dataset/generating_train_bev.py:34-35) and typical footprints (w, l) in metres
+BOX_CLASSES = ["car", "motorcycle", "bus", "bicycle", "truck", "pedestrian", "other_vehicle", "animal",
+               "emergency_vehicle"]
+_BOX_WL = [(1.93, 4.76), (0.96, 2.35), (2.96, 12.34), (0.63, 1.76), (2.84, 10.24), (0.77, 0.81), (2.79, 8.20),
+           (0.36, 0.73), (2.45, 6.52)]
+BOX_SCALE = 0.8   # generating_train_bev.py:40
+
+
+def box_scene(seed, n_boxes=60, extent=75.0):
+    """Seeded annotation set of one sample in car space: (corners, class_ids) with corners (n, 3, 4)
+    float64 = Box.bottom_corners() of every box (four bottom corners in order around the footprint,
+    box sizes already scaled by BOX_SCALE, generating_train_bev.py:119-125) and class_ids (n,) the index
+    into BOX_CLASSES.  Centres reach beyond the 336 x 0.4 m image so that some boxes are clipped."""
+    rng = np.random.default_rng(seed)
+    cls = rng.integers(0, len(BOX_CLASSES), n_boxes)
+    corners = np.zeros((n_boxes, 3, 4), dtype=np.float64)
+    for i, c in enumerate(cls):
+        w, l = np.array(_BOX_WL[c]) * BOX_SCALE * rng.uniform(0.8, 1.25)
+        yaw = rng.uniform(-np.pi, np.pi)
+        centre = rng.uniform(-extent, extent, 2)
+        z = rng.uniform(-2.5, -0.5)
+        local = np.array([[l / 2, w / 2], [l / 2, -w / 2], [-l / 2, -w / 2], [-l / 2, w / 2]])
+        rot = np.array([[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]])
+        xy = local @ rot.T + centre
+        corners[i, 0], corners[i, 1], corners[i, 2] = xy[:, 0], xy[:, 1], z
+    return corners, cls.astype(np.int32)

@@ -128,3 +128,45 @@ def run_second_get_sensor_points(info):
     ns = {"np": np, "Path": Path, "info": info}
     exec(compile(src, path, "exec"), ns)
     return ns["points"]
+
+
+def run_bev_draw_boxes(im, voxel_size, corners, class_ids, classes, z_offset=0.0):
+    """Executes the reference's own ``draw_boxes`` (generating-dataset/generating_train_bev.py:127-139)
+    together with the helpers it calls (:47-82) on `im` (H, W, 3) float32, in place.  They are nested
+    closures of ``main``, so their source lines are read from the reference file,
+    dedented and executed unchanged; only ``np.int0`` (removed in numpy 2) is aliased to ``np.intp``.
+    The boxes are stand-ins that offer what draw_boxes reads: ``bottom_corners()`` and ``name``."""
+    import textwrap
+    import types
+
+    import cv2
+    import numpy as np
+    path = os.path.join(REF, "generating-dataset", "generating_train_bev.py")
+    with open(path) as f:
+        lines = f.readlines()
+
+    def block(name):
+        start = next(i for i, l in enumerate(lines) if l.lstrip().startswith("def %s(" % name))
+        indent = len(lines[start]) - len(lines[start].lstrip())
+        end = start + 1
+        while end < len(lines) and (not lines[end].strip() or len(lines[end]) - len(lines[end].lstrip()) > indent):
+            end += 1
+        return textwrap.dedent("".join(lines[start:end]))
+
+    npx = types.SimpleNamespace(**{k: getattr(np, k) for k in dir(np) if not k.startswith("__")})
+    npx.int0 = np.intp
+    ns = {"np": npx, "cv2": cv2}
+    for name in ("create_transformation_matrix_to_voxel_space", "transform_points", "car_to_voxel_coords",
+                 "draw_boxes"):
+        exec(compile(block(name), path, "exec"), ns)
+
+    class _Box:
+        def __init__(self, c, name):
+            self._c, self.name = c, name
+
+        def bottom_corners(self):
+            return self._c
+
+    boxes = [_Box(np.asarray(c, dtype=np.float64), classes[int(k)]) for c, k in zip(corners, class_ids)]
+    ns["draw_boxes"](im, voxel_size, boxes=boxes, classes=classes, z_offset=z_offset)
+    return im
