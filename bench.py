@@ -185,6 +185,20 @@ def time_other_configs(dev, reps=10):
                                             n_frames=1, want=("u8", "chw"), map_u8=maps, out=res))
     out["C4 BEV 1024x1024x3, 20 sweeps with 4x4, u8 + (6,1024,1024) CHW with map"] = {
         "points": n, "ms": round(ms, 4), "points_per_s": round(n / (ms * 1e-3))}
+    # block-filtering voxelizer (all.fhd.config) on the same cloud; target raster of 128 frames
+    fhd_vs, fhd_rg = (0.05, 0.05, 0.2), (-50, -50, -5, 50, 50, 3)
+    ms = timed(lambda: vg.voxelize_frames(cloud, offs, fhd_vs, fhd_rg, 5, 60000, zero_tail=False,
+                                          block_filter=(1, 8, 0.2, 2.0)))
+    out["n4 block-filtering voxelizer 0.05 m, T=5, V=60000, block 1x8, 0.2 m"] = {
+        "points": n, "ms": round(ms, 4), "points_per_s": round(n / (ms * 1e-3))}
+    scenes = [synth.box_scene(7000 + f, 60) for f in range(128)]
+    d_c = torch.from_numpy(np.concatenate([c for c, _ in scenes])).to(dev)
+    d_k = torch.from_numpy(np.concatenate([k + 1 for _, k in scenes]).astype(np.int32)).to(dev)
+    box_offs = np.arange(129, dtype=np.int64) * 60
+    ms = timed(lambda: bev.rasterize_targets(d_c, d_k, box_offs, synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE,
+                                             synth.BEV_Z_OFFSET))
+    out["n4 target raster (draw_boxes) 128 frames x 60 boxes, 336x336"] = {
+        "boxes": 128 * 60, "ms": round(ms, 4), "frames_per_s": round(128 / (ms * 1e-3))}
     return out
 
 

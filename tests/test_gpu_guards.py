@@ -130,3 +130,47 @@ def test_padded_voxelize_bev_and_ingest(env):
                                        0, -1.0, cols, out.t.data_ptr(), st))
         torch.cuda.synchronize()
         assert out.intact() and bool((out.t != SENT_F).all())
+
+
+def test_block_filter_and_target_raster_stay_inside(env):
+    torch, nat, lib, h, make_cfg = env
+    from lyft3d_b200.voxel_generator import _make_filter
+    dev = torch.device("cuda", 0)
+    st = nat.current_stream_ptr(dev)
+    F, T, V = 3, 3, 9000          # V is hit by the larger frames
+    frames = [synth.c5_frame(600 + f)[: 15000 + 15000 * f] for f in range(F)]
+    pts = torch.from_numpy(np.concatenate(frames)).to(dev)
+    offs = np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]).astype(np.int64)
+    vs, rg = (0.05, 0.05, 0.2), (-50, -50, -5, 50, 50, 3)
+    for zero_tail in (False, True):
+        cfg = make_cfg(vs, rg, T, V, 4, "continue", zero_tail)
+        flt = _make_filter((1, 8, 0.2, 2.0))
+        vox = Guarded((F, V, T, 4), torch.float32, dev)
+        coords = Guarded((F, V, 3), torch.int32, dev)
+        num = Guarded((F, V), torch.int32, dev)
+        vnum = Guarded((F,), torch.int32, dev)
+        mask = Guarded((F, V), torch.int32, dev)
+        nat.check(lib.lv_voxelize_filtered(h.ptr, ctypes.byref(cfg), ctypes.byref(flt), pts.data_ptr(), F,
+                                           offs.ctypes.data, vox.t.data_ptr(), coords.t.data_ptr(), num.t.data_ptr(),
+                                           vnum.t.data_ptr(), mask.t.data_ptr(), st))
+        torch.cuda.synchronize()
+        for g in (vox, coords, num, vnum, mask):
+            assert g.intact()
+        k = vnum.t.cpu().numpy()
+        assert (k > 0).all() and (k < V).all()
+        if not zero_tail:      # rows at and beyond the survivors are left untouched
+            for f in range(F):
+                assert bool((vox.t[f, k[f]:] == SENT_F).all()) and bool((num.t[f, k[f]:] == SENT_I).all())
+    # target raster: frames with 0, 1 and many boxes, boxes far outside the image
+    corners, cls = synth.box_scene(42, 70, 120.0)
+    box_offs = np.array([0, 0, 1, 70], dtype=np.int64)
+    d_c = torch.from_numpy(corners).to(dev)
+    d_k = torch.from_numpy(cls + 1).to(dev)
+    shp = (ctypes.c_int32 * 3)(201, 157, 3)
+    vsz = (ctypes.c_double * 3)(0.4, 0.4, 1.5)
+    tgt = Guarded((3, 201, 157), torch.uint8, dev)
+    nat.check(lib.lv_draw_boxes(h.ptr, d_c.data_ptr(), d_k.data_ptr(), 3, box_offs.ctypes.data, shp, vsz, -2.0,
+                                tgt.t.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert tgt.intact()
+    assert not tgt.t[0].any() and tgt.t[2].any() and int(tgt.t.max()) <= 9
