@@ -75,6 +75,8 @@ struct lv_handle {
                                       // 0.203 vs 0.158 ms stride 5, 128 frames) - the kernel is bound by the
                                       // L2 atomics, not by the loads
 
+  int64_t canvas_variant = 0;         // 0 = auto (pillar_canvas_q_kernel when the shape allows), 1 = pillar_canvas_kernel (A/B)
+
   // BEV
   lv_buffer bev_counts;               // u32 [frames_in_flight][cells], kept all-zero between calls
   lv_buffer bev_dirty;                // 1 bit per 4 counts, kept all-zero between calls

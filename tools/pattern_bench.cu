@@ -58,6 +58,79 @@ __global__ void __launch_bounds__(256) k_persistent(float* out, const int* map) 
   }
 }
 
+// ---- TMA store variants: the SM only issues copies, the copy engine streams the rows out of shared memory.
+// F: per tile, one warp issues 64 one-dimensional bulk stores of 512 B (cp.async.bulk.global.shared::cta) from a
+//    zero buffer, behind the map load.  G: per tile ONE two-dimensional tensor store (box 128 cells x 64 rows =
+//    32 KB) from a ring of NBUF shared-memory tiles; a buffer is reused once its bulk group has been read.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_store_1d(void* g, const void* s, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(smem_u32(s)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(128) k_tma1d(float* out, const int* map) {
+  __shared__ __align__(128) float zero[128];
+  const int tiles = NCELL / 128, total = tiles * B;
+  zero[threadIdx.x] = 0.f;
+  fence_async_smem();
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // every warp owns a quarter of the CTA's tiles
+  for (int tile = blockIdx.x * 4 + warp; tile < total; tile += gridDim.x * 4) {
+    const int b = tile / tiles, t = tile - b * tiles;
+    const int4 m = *reinterpret_cast<const int4*>(map + (size_t)b * NCELL + t * 128 + lane * 4);
+    const int any = __any_sync(0xffffffffu, (m.x & m.y & m.z & m.w) >= 0);
+    float* dst = out + (size_t)b * C * NCELL + (size_t)t * 128;
+    if (!any || true) {
+      bulk_store_1d(dst + (size_t)lane * NCELL, zero, 512);
+      bulk_store_1d(dst + (size_t)(lane + 32) * NCELL, zero, 512);
+      bulk_commit();
+    }
+  }
+  bulk_wait_read<0>();
+}
+
+#include <cuda.h>
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+__device__ __forceinline__ void tensor_store_2d(const CUtensorMap* tm, int x, int y, const void* s) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(x), "r"(y),
+               "r"(smem_u32(s))
+               : "memory");
+}
+
+template <int NBUF, int ROWS>
+__global__ void __launch_bounds__(128) k_tma2d(const __grid_constant__ CUtensorMap tm, const int* map) {
+  extern __shared__ __align__(128) float buf[];   // NBUF x ROWS x 128 floats
+  const int per = ROWS * 128;
+  const int tiles = NCELL / 128, total = tiles * B * (C / ROWS);
+  for (int i = threadIdx.x; i < NBUF * per; i += 128) buf[i] = 0.f;
+  fence_async_smem();
+  __syncthreads();
+  int it = 0;
+  for (int job = blockIdx.x; job < total; job += gridDim.x, ++it) {
+    const int tile = job / (C / ROWS), part = job - tile * (C / ROWS);
+    const int b = tile / tiles, t = tile - b * tiles;
+    float* cur = buf + (it % NBUF) * per;
+    const int mv = threadIdx.x < 128 ? map[(size_t)b * NCELL + t * 128 + threadIdx.x] : -1;
+    if (threadIdx.x == 0) bulk_wait_read<NBUF - 1>();     // the buffer's previous store has been read
+    __syncthreads();
+    if (mv >= 0) cur[threadIdx.x] = 1.f;                  // stand-in for the feature scatter
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tensor_store_2d(&tm, t * 128, b * C + part * ROWS, cur);
+      bulk_commit();
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_read<0>();
+}
+
 template <typename F>
 static void run(const char* name, F f) {
   cudaEvent_t a, b;
@@ -89,5 +162,33 @@ int main() {
   run("E persistent tiles (6/SM), map prefetched", [&] { k_persistent<<<148 * 6, 256>>>(out, map); });
   run("E persistent tiles (4/SM), map prefetched", [&] { k_persistent<<<148 * 4, 256>>>(out, map); });
   run("E persistent tiles (8/SM), map prefetched", [&] { k_persistent<<<148 * 8, 256>>>(out, map); });
+  for (int per_sm : {2, 4, 8, 16}) {
+    char name[96];
+    snprintf(name, sizeof(name), "F 1D bulk stores 64 x 512 B, %d CTAs/SM", per_sm);
+    run(name, [&] { k_tma1d<<<148 * per_sm, 128>>>(out, map); });
+  }
+  {
+    EncodeTiled enc = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&enc, cudaEnableDefault, &qr);
+    auto make = [&](int rows) {
+      CUtensorMap tm;
+      cuuint64_t dims[2] = {NCELL, (cuuint64_t)B * C};
+      cuuint64_t strides[1] = {(cuuint64_t)NCELL * 4};
+      cuuint32_t box[2] = {128, (cuuint32_t)rows};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) printf("cuTensorMapEncodeTiled failed: %d\n", (int)r);
+      return tm;
+    };
+    CUtensorMap tm64 = make(64), tm16 = make(16);
+    cudaFuncSetAttribute(k_tma2d<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * 512);
+    cudaFuncSetAttribute(k_tma2d<6, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 64 * 512);
+    cudaFuncSetAttribute(k_tma2d<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16 * 512);
+    run("G 2D tensor store 32 KB, 3 buffers, 2 CTAs/SM", [&] { k_tma2d<3, 64><<<148 * 2, 128, 3 * 64 * 512>>>(tm64, map); });
+    run("G 2D tensor store 32 KB, 6 buffers, 1 CTA/SM", [&] { k_tma2d<6, 64><<<148, 128, 6 * 64 * 512>>>(tm64, map); });
+    run("G 2D tensor store 8 KB, 4 buffers, 6 CTAs/SM", [&] { k_tma2d<4, 16><<<148 * 6, 128, 4 * 16 * 512>>>(tm16, map); });
+  }
   return 0;
 }
