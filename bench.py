@@ -455,7 +455,7 @@ def main():
         kernel_names = {"bev": "bev_hist_kernel + bev_finalize_flat4_kernel",
                         "voxelize": "vx_cells/assign/keys/scan_hist/scatter + vx_bins_kernel<voxels>",
                         "decorate": "pillar_decorate_fast_kernel",
-                        "scatter": "pillar_canvas_kernel (+ pillar_index_kernel, 1.5% of the stage)",
+                        "scatter": "pillar_canvas_q_kernel (+ pillar_index_kernel, 1.5% of the stage)",
                         "pillarize": "vx_cells/assign/keys/scan_hist/scatter + vx_bins_kernel<decorate>"}
         # DRAM traffic of the dominant kernel per launch from the committed ncu --set full capture
         # (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum at this workload)
