@@ -12,8 +12,9 @@
 //     scanline edges sorted by their 16.16 fixed-point x = x0 + (y - y0) * dx.
 //   DB1 db_setup   one thread per box: fp64 voxel-space affine of the four corners (un-fused multiply, add - the
 //                  BEV rule), C truncation, clipLine per edge, line and scanline-edge records
-//   DB2 db_raster  one thread per pixel: boxes from last to first, the first that covers the pixel wins;
-//                  every byte of the (H, W) uint8 target is written exactly once (0 = background)
+//   DB2 db_raster  one CTA per 8 x 32 pixel tile: the boxes whose vertex bounding box meets the tile are collected in
+//                  shared memory (descending order), then one thread per pixel walks them - the first that covers
+//                  the pixel wins; every byte of the (H, W) uint8 target is written exactly once (0 = background)
 #include "lv_common.cuh"
 
 namespace {
@@ -25,7 +26,7 @@ constexpr long long DB_COORD_LIMIT = 1ll << 20;   // vertices are clamped to +-2
 struct DbLine { int valid, xs, ys, D, d, sy, vert, pad; };
 struct DbEdge { int y0, y1; long long x, dx; };
 struct DbBox {
-  int color, vy_min, vy_max, fy0, fy1, pad[3];
+  int color, vy_min, vy_max, fy0, fy1, vx_min, vx_max, pad;
   DbLine line[4];
   DbEdge edge[4];
 };
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(DB_THREADS) db_setup_kernel(DbParams p) {
   }
   DbBox r;
   r.color = p.colors[b];
-  r.pad[0] = r.pad[1] = r.pad[2] = 0;
+  r.pad = 0;
   long long ymn = vy[0], ymx = vy[0];
 #pragma unroll
   for (int k = 1; k < 4; ++k) {
@@ -107,6 +108,16 @@ __global__ void __launch_bounds__(DB_THREADS) db_setup_kernel(DbParams p) {
   }
   r.vy_min = (int)(ymn < 0 ? 0 : ymn);
   r.vy_max = (int)(ymx > p.H - 1 ? p.H - 1 : ymx);
+  long long xmn = vx[0], xmx = vx[0];
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    xmn = vx[k] < xmn ? vx[k] : xmn;
+    xmx = vx[k] > xmx ? vx[k] : xmx;
+  }
+  // every painted pixel lies inside the vertex bounding box (clipped end points stay on their segment, the
+  // truncated slopes never overshoot a vertex on an image row); one pixel of slack on either side
+  r.vx_min = (int)(xmn - 1 < 0 ? 0 : xmn - 1);
+  r.vx_max = (int)(xmx + 1 > p.W - 1 ? p.W - 1 : xmx + 1);
   long long fy0 = (1ll << 40), fy1 = -(1ll << 40);
   int n_edges = 0;
 #pragma unroll
@@ -195,14 +206,61 @@ __device__ __forceinline__ bool db_filled(const DbBox& r, int x, int y) {
   return false;
 }
 
-// grid (pixel blocks, frames)
-__global__ void __launch_bounds__(DB_THREADS) db_raster_kernel(DbParams p) {
+// grid (tiles of DB_TH x DB_TW pixels, frames).  The CTA first collects, in descending box order, the boxes whose
+// vertex bounding box meets its tile (one thread per box, ballot compaction), then every thread walks that short
+// list for its pixel: the first hit is the last box painted.
+constexpr int DB_TW = 32, DB_TH = DB_THREADS / DB_TW;
+constexpr int DB_LIST = 1024;   // candidates kept in shared memory; a fuller tile falls back to the global walk
+
+__global__ void __launch_bounds__(DB_THREADS) db_raster_kernel(DbParams p, int tiles_x) {
+  __shared__ int s_list[DB_LIST];
+  __shared__ int s_warp[DB_THREADS / 32];
+  __shared__ int s_n;
   const int f = blockIdx.y;
   const int64_t b0 = p.box_off[f], b1 = p.box_off[f + 1];
-  const int npix = p.H * p.W;
-  for (int pix = blockIdx.x * DB_THREADS + threadIdx.x; pix < npix; pix += gridDim.x * DB_THREADS) {
-    const int y = pix / p.W, x = pix - y * p.W;
-    int color = 0;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int ya = ty * DB_TH, xa = tx * DB_TW;
+  const int yb = min(ya + DB_TH, p.H) - 1, xb = min(xa + DB_TW, p.W) - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  bool overflow = false;
+  for (int64_t hi = b1; hi > b0; hi -= DB_THREADS) {       // chunks of boxes, last chunk first
+    const int64_t b = hi - 1 - threadIdx.x;                // thread 0 looks at the last box of the chunk
+    bool keep = false;
+    if (b >= b0) {
+      const DbBox& r = p.recs[b];
+      keep = r.vy_min <= yb && r.vy_max >= ya && r.vx_min <= xb && r.vx_max >= xa;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_n;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const int pos = before + __popc(bal & ((1u << lane) - 1u));
+    if (keep && pos < DB_LIST) s_list[pos] = (int)(b - b0);
+    __syncthreads();
+    if (threadIdx.x == DB_THREADS - 1) s_n = before + __popc(bal);
+    __syncthreads();
+    if (s_n > DB_LIST) { overflow = true; break; }         // uniform: s_n is shared
+  }
+  const int y = ya + threadIdx.x / DB_TW, x = xa + (threadIdx.x % DB_TW);
+  if (y >= p.H || x >= p.W) return;
+  int color = 0;
+  if (!overflow) {
+    const int n = s_n;
+    for (int k = 0; k < n; ++k) {
+      const DbBox& r = p.recs[b0 + s_list[k]];
+      if (y < r.vy_min || y > r.vy_max) continue;
+      bool hit = db_filled(r, x, y);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hit = hit || db_on_line(r.line[i], x, y);
+      if (hit) {
+        color = r.color;
+        break;
+      }
+    }
+  } else {
     for (int64_t b = b1 - 1; b >= b0; --b) {
       const DbBox& r = p.recs[b];
       if (y < r.vy_min || y > r.vy_max) continue;
@@ -214,8 +272,8 @@ __global__ void __launch_bounds__(DB_THREADS) db_raster_kernel(DbParams p) {
         break;
       }
     }
-    p.target[(int64_t)f * npix + pix] = (uint8_t)color;
   }
+  p.target[((int64_t)f * p.H + y) * p.W + x] = (uint8_t)color;
 }
 
 }  // namespace
@@ -257,11 +315,9 @@ extern "C" int lv_draw_boxes(lv_handle* h, const double* d_corners, const int32_
     db_setup_kernel<<<(unsigned)lv_div_up(n_boxes, DB_THREADS), DB_THREADS, 0, stream>>>(p);
     LV_LAUNCH_CHECK(h);
   }
-  int gx = (int)lv_div_up((int64_t)p.H * p.W, DB_THREADS);
-  const int cap = (int)lv_div_up((int64_t)h->num_sms * 8, n_frames);
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  db_raster_kernel<<<dim3((unsigned)gx, (unsigned)n_frames), DB_THREADS, 0, stream>>>(p);
+  const int tiles_x = (int)lv_div_up(p.W, DB_TW), tiles_y = (int)lv_div_up(p.H, DB_TH);
+  LV_REQUIRE(n_frames <= 65535, "lv_draw_boxes: at most 65535 frames per call");
+  db_raster_kernel<<<dim3((unsigned)(tiles_x * tiles_y), (unsigned)n_frames), DB_THREADS, 0, stream>>>(p, tiles_x);
   LV_LAUNCH_CHECK(h);
   return LV_OK;
 }

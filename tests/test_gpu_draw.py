@@ -94,3 +94,17 @@ def test_painters_order_and_errors(bev):
     with pytest.raises(ValueError):
         bev.draw_boxes(np.zeros(synth.BEV_SHAPE, np.float32), synth.BEV_VOXEL_SIZE, [_Box(big, "tram")],
                        synth.BOX_CLASSES)
+
+
+def test_more_candidates_than_the_shared_list(bev):
+    """> 1024 boxes meeting one tile: the kernel falls back to walking every box of the frame."""
+    from oracle import draw_oracle
+    rng = np.random.default_rng(5)
+    n = 1300
+    c, k = synth.box_scene(900, n, 3.0)            # all centres within 3 m of the origin
+    shape, vs = (96, 96, 3), (0.4, 0.4, 1.5)
+    out = bev.rasterize_targets(c, k + 1, np.array([0, n], dtype=np.int64), shape, vs, 0.0)[0]
+    ref = np.zeros(shape, dtype=np.float32)
+    draw_oracle.draw_boxes(ref, vs, list(c), list(k + 1), 0.0)
+    assert np.array_equal(out, ref[:, :, 0].astype(np.uint8))
+    assert rng is not None
