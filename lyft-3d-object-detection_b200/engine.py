@@ -13,6 +13,7 @@ f mod G; there is no collective on the hot path.  All buffers are preallocated
 once ("rotating arena"), so a steady-state step performs no allocation.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -20,6 +21,9 @@ import torch
 from . import _native as nat
 from . import synth
 from .voxel_generator import _make_config
+
+
+_NVTX = os.environ.get("LV_NVTX", "") not in ("", "0")
 
 
 def shard_frames(n_frames, rank, world_size):
@@ -170,19 +174,36 @@ class FrameBatchEngine:
             self.canvas.data_ptr(), st))
 
     def step(self, points, pfn=None, fused=True):
-        """One pass of both paths over a (F*n, 4) float32 CUDA tensor of points."""
+        """One pass of both paths over a (F*n, 4) float32 CUDA tensor of points.  With LV_NVTX=1 the
+        stages carry NVTX ranges named after the reference's own timers:
+        "voxel_gene_time" (data/preprocess.py:303-318), "voxel_feature_extractor" and "middle forward"
+        (models/voxelnet.py:326-334), so that a timeline lines up with the reference's numbers."""
+        nvtx = _NVTX
+        if nvtx:
+            torch.cuda.nvtx.range_push("bev create_voxel_pointcloud")
         self.bev(points)
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push("voxel_gene_time")
         if fused:
             self.pillarize(points)
             rows = self.read_total_rows()
         else:
             self.voxelize(points)
             rows = self.read_total_rows()
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_push("voxel_feature_extractor")
             self.decorate(rows)
         feats = None
         if pfn is not None:
             feats = pfn(self.decorated[:rows])
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push("middle forward")
         self.scatter(rows, feats)
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
         return rows
 
 
