@@ -50,6 +50,9 @@
 #define VX_DROPPED 0xffffffffu
 #define VX_MAX_BINS 2048
 #define VX_MAX_LOW_BITS 10
+#ifndef VX_BINS_MINB
+#define VX_BINS_MINB 4   // CTAs per SM of the voxel / decorate / mean modes of vx_bins_kernel (64 registers)
+#endif
 
 struct VoxParams {
   const float* pts;            // (N_total, C)
@@ -85,6 +88,7 @@ struct VoxParams {
   int concat;                  // 1: frames back to back, coords carry the batch index (coord_cols == 4)
   int coord_cols;              // 3 (z,y,x) or 4 (b,z,y,x)
   int64_t capacity;            // output rows available
+  unsigned long long* prof;    // VX_PROFILE builds: [4] accumulated clocks of the bins kernel phases + [4] CTA count
 };
 
 struct ChunkLoc {
@@ -459,7 +463,7 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p) {
 #define VX_OUT_PFN 2        // decoration + PFNLayer (inference) fused into the gather: (rows, units) features
 #define VX_OUT_MEAN 3       // SimpleVoxel mean VFE (voxel_encoder.py:219-225) fused into the gather
 template <int MODE, bool C4>
-__global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bins_kernel(VoxParams p, DecoCfg d, float* __restrict__ decorated,
+__global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : VX_BINS_MINB) vx_bins_kernel(VoxParams p, DecoCfg d, float* __restrict__ decorated,
                                                                 PfnCfg pfn) {
   constexpr bool DECO = MODE == VX_OUT_DECORATE || MODE == VX_OUT_PFN;
   extern __shared__ __align__(16) int smem[];
@@ -473,6 +477,9 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
 
   const int fl = blockIdx.y, f = p.f0 + fl, b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef VX_PROFILE
+  const long long tp0 = clock64();
+#endif
   const int vnum = p.voxel_num[f];
   if ((b << p.low_bits) >= vnum && b != 0) return;  // bin beyond the last voxel: nothing to do
   // first output row of the frame: prefix of voxel_num over the earlier frames of the batch
@@ -512,6 +519,9 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
     total[i] = 0;
     s_cell[i] = i < nv ? p.creator_cell[(fstart - p.pt_lo) + v0 + i] : 0;   // in flight during phase 1
   }
+#ifdef VX_PROFILE
+  const long long tp1 = clock64();
+#endif
   const unsigned lt = lv_lanemask_lt();
   const unsigned lowmask = NV - 1;
   // ---- phase 1: stable rank by voxel inside the bin, tile by tile (2048 points) ----
@@ -574,6 +584,21 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : 4) vx_bin
     __syncthreads();
   }
   __syncthreads();
+#ifdef VX_PROFILE
+  const long long tp2 = clock64();
+  struct ProfEnd {
+    unsigned long long* prof; long long t0, t1, t2;
+    __device__ ~ProfEnd() {
+      if (prof && threadIdx.x == 0) {
+        const long long t3 = clock64();
+        atomicAdd(prof + 0, (unsigned long long)(t1 - t0));
+        atomicAdd(prof + 1, (unsigned long long)(t2 - t1));
+        atomicAdd(prof + 2, (unsigned long long)(t3 - t2));
+        atomicAdd(prof + 3, 1ull);
+      }
+    }
+  } prof_end{p.prof, tp0, tp1, tp2};
+#endif
   // ---- phase 2: the output rows of the bin (contiguous in memory) ----
   const long long row0 = s_row0;
   if (row0 + v0 + nv > p.capacity) nv = (int)(p.capacity - (row0 + v0) > 0 ? p.capacity - (row0 + v0) : 0);
@@ -976,6 +1001,18 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   else if (out4) LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_VOXELS, true>, smem_bins));
   else LV_CHECK(vx_set_smem(vx_bins_kernel<VX_OUT_VOXELS, false>, smem_bins));
   p.row_div_m = (unsigned)(((1ull << 32) + (uint32_t)T - 1) / (uint32_t)T);
+#ifdef VX_PROFILE
+  static unsigned long long* d_prof = nullptr;
+  if (!d_prof) { cudaMalloc(&d_prof, 64); cudaMemset(d_prof, 0, 64); }
+  p.prof = d_prof;
+  {
+    unsigned long long hp[4];
+    cudaMemcpy(hp, d_prof, 32, cudaMemcpyDeviceToHost);
+    if (hp[3]) fprintf(stderr, "[vx_bins profile] CTAs %llu  prologue %.0f  phase1 %.0f  phase2 %.0f clocks per CTA (thread 0)\n", hp[3],
+                       (double)hp[0] / hp[3], (double)hp[1] / hp[3], (double)hp[2] / hp[3]);
+    cudaMemset(d_prof, 0, 64);
+  }
+#endif
 
   int f0 = 0;
   while (f0 < n_frames) {
