@@ -165,6 +165,10 @@ int lv_set_option(lv_handle* h, const char* name, int64_t value) {
     h->disable_tma = value;
     return LV_OK;
   }
+  if (strcmp(name, "vox_frame_kernel") == 0) {
+    h->vox_frame_kernel = value;
+    return LV_OK;
+  }
   if (strcmp(name, "canvas_variant") == 0) {
     h->canvas_variant = value;
     return LV_OK;

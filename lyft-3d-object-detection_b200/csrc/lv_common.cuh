@@ -75,6 +75,9 @@ struct lv_handle {
                                       // 0.203 vs 0.158 ms stride 5, 128 frames) - the kernel is bound by the
                                       // L2 atomics, not by the loads
 
+  int64_t vox_frame_kernel = 0;       // 1: small grids run K1-K5 in one cluster per frame (vx_frame_kernel, distributed shared
+                                      // memory map).  Off by default: measured slower than the five kernels (0.71 vs 0.67 ms per
+                                      // 128 pillar frames) - scattered 4-byte DSMEM accesses run at ~0.5 per cycle and SM
   int64_t canvas_variant = 0;         // 0 = auto (pillar_canvas_q_kernel when the shape allows), 1 = pillar_canvas_kernel (A/B)
 
   // BEV

@@ -38,8 +38,12 @@
 // Algorithmic bytes: 4*C per point read + V*(T*C*4 + 16) written (T*C_out*4 when fused).
 #include <math.h>
 
+#include <cooperative_groups.h>
+
 #include "lv_common.cuh"
 #include "lv_decorate.cuh"
+
+namespace cg = cooperative_groups;
 
 #define VX_THREADS 256
 #define VX_WARPS (VX_THREADS / 32)
@@ -453,6 +457,246 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p) {
     p.keys[pos] = key[r];
     p.vals[pos] = base + r * 32 + lane;
   }
+}
+
+// ---------------------------------------------------------------- KF: K1-K5 of one frame inside a thread-block cluster
+// Small grids (the pillar configs: 400 x 400 x 1 cells) fit the dense first[] map of a frame into the shared memory
+// of a cluster of CS CTAs (distributed shared memory): cell c lives in CTA c / part at offset c % part.  One cluster
+// of CS x 1024 threads then does K1-K5 for its frame without a single L2 atomic or map gather:
+//   A  map := EMPTY                                                                  (cluster barrier)
+//   B  cell(i); atomicMin(map[cell], i) on the owner CTA's shared memory             (cluster barrier)
+//   C  creator(i) = map[cell(i)] == i; creators per warp -> wtot[] of every CTA      (cluster barrier)
+//   D  rank = exclusive count of earlier creators; map[cell] := ~rank, creator_cell, voxel_num, cut      (barrier)
+//   E  vid = ~map[cell]; key; stable rank inside the warp per bin (match_any + per-warp counters)
+//   F  counters -> bases: exclusive over the warps of the CTA, CTA totals to every CTA (barrier), over CTAs, bins
+//   G  keys / vals scattered to their bin positions (what K5 writes), bin table and frame_kept for K6
+// Warp w of the cluster owns the contiguous points [w * span, (w + 1) * span), round by round, so (warp, round,
+// lane) order is point order.  The map never exists in global memory, so there is nothing to reset.
+// OPT-IN (lv_set_option "vox_frame_kernel" 1): bit-identical to K1-K5 (tests/test_gpu_voxel.py runs both), but
+// measured SLOWER on 128 C5 frames - 0.71 vs 0.67 ms for the pillarize stage.  clock64 per phase (-DVX_PROFILE),
+// one cluster of 4 x 1024 threads per 53,146-point frame: A 2.8k, B 37k, C 14k, D 10k, E 15k, F 9.5k, G 7k clocks
+// = 49 us per frame, 33 clusters at a time.  The scattered 4-byte remote shared-memory operations (three of four
+// cells live in another CTA) run at roughly one per two cycles and SM; a variant that partitions the POINTS by
+// owner CTA so that every map access is local is the next thing to try.
+#define VF_THREADS 1024
+#define VF_WARPS (VF_THREADS / 32)
+#define VF_MAX_CS 8
+#define VF_ROUNDS 16   // rounds of 32 points a warp keeps in registers: frames of up to CS x 16,384 points
+
+__device__ __forceinline__ int* vf_remote(cg::cluster_group& cluster, int* map, int cell, int part) {
+  const int owner = cell / part;
+  return cluster.map_shared_rank(map + (cell - owner * part), owner);
+}
+
+template <bool C4>
+__global__ void __launch_bounds__(VF_THREADS, 1) vx_frame_kernel(VoxParams p, int part) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+  const int fl = blockIdx.x / CS, f = p.f0 + fl;
+  const int D = p.n_bins;
+  extern __shared__ int fsm[];
+  int* map = fsm;                         // [part]
+  int* cnt = map + part;                  // [32][D]
+  int* ctot = cnt + VF_WARPS * D;         // [VF_MAX_CS][D]  per-CTA bin totals, replicated in every CTA
+  int* dbase = ctot + VF_MAX_CS * D;      // [D]
+  int* wtot = dbase + D;                  // [VF_MAX_CS * 32] creators per warp, replicated in every CTA
+  int* misc = wtot + VF_MAX_CS * VF_WARPS;  // [0] break cut-off
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = crank * VF_WARPS + warp, NW = CS * VF_WARPS;
+  const int64_t start = __ldg(p.frame_off + f);
+  const int n = (int)(__ldg(p.frame_off + f + 1) - start);
+  const int span = (((n + NW - 1) / NW) + 31) & ~31;
+  const int lo = gw * span;
+  const int hi = min(lo + span, n);       // rounds: base = lo, lo + 32, ... < hi
+  const int64_t wi0 = start - p.pt_lo;    // workspace index of the frame's first point
+  const unsigned lt = lv_lanemask_lt();
+
+#ifdef VX_PROFILE
+  long long tq[8]; int nq = 0;
+#define VF_MARK() tq[nq++] = clock64()
+#else
+#define VF_MARK()
+#endif
+  VF_MARK();
+  // ---- A
+  for (int i = threadIdx.x; i < part; i += VF_THREADS) map[i] = VX_EMPTY;
+  for (int i = threadIdx.x; i < VF_WARPS * D; i += VF_THREADS) cnt[i] = 0;
+  if (threadIdx.x == 0) misc[0] = 0x7fffffff;
+  cluster.sync();
+  VF_MARK();
+
+  // ---- B: the warp's points stay in registers from here on (VF_ROUNDS rounds of 32: the host checks the span)
+  int cell[VF_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < VF_ROUNDS; ++r) {
+    const int li = lo + r * 32 + lane;
+    cell[r] = -1;
+    if (li < hi) {
+      const int64_t gi = start + li;
+      float x, y, z;
+      if (C4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.pts) + gi);
+        x = v.x; y = v.y; z = v.z;
+      } else {
+        const float* q = p.pts + gi * p.C;
+        x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
+      }
+      // simplevis.py:38-42: c = floor((p - lo) / vs) in float32, bounds on the float
+      const float cx = floorf(__fdiv_rn(__fsub_rn(x, p.lo[0]), p.vs[0]));
+      const float cy = floorf(__fdiv_rn(__fsub_rn(y, p.lo[1]), p.vs[1]));
+      const float cz = floorf(__fdiv_rn(__fsub_rn(z, p.lo[2]), p.vs[2]));
+      if (cx >= 0.f && cx < (float)p.grid[0] && cy >= 0.f && cy < (float)p.grid[1] && cz >= 0.f &&
+          cz < (float)p.grid[2])
+        cell[r] = ((int)cz * p.grid[1] + (int)cy) * p.grid[0] + (int)cx;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < VF_ROUNDS; ++r) {
+    if (lo + r * 32 >= hi) break;   // warp-uniform
+    const unsigned peers = __match_any_sync(0xffffffffu, cell[r]);
+    if (cell[r] >= 0 && lane == __ffs(peers) - 1) atomicMin(vf_remote(cluster, map, cell[r], part), lo + r * 32 + lane);
+  }
+  cluster.sync();
+  VF_MARK();
+
+  // ---- C: creator flags, one bit per round
+  unsigned creator = 0;
+  {
+    int first[VF_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < VF_ROUNDS; ++r) first[r] = cell[r] >= 0 ? *vf_remote(cluster, map, cell[r], part) : -1;
+#pragma unroll
+    for (int r = 0; r < VF_ROUNDS; ++r)
+      if (cell[r] >= 0 && first[r] == lo + r * 32 + lane) creator |= 1u << r;
+  }
+  int mine = __popc(creator);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane < CS) cluster.map_shared_rank(wtot, lane)[gw] = mine;
+  cluster.sync();
+  VF_MARK();
+
+  // ---- D: voxel ids in first-come order
+  int excl = 0;
+  for (int w = lane; w < gw; w += 32) excl += wtot[w];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) excl += __shfl_xor_sync(0xffffffffu, excl, o);
+  if (gw == NW - 1 && lane == 0) {
+    const int total = excl + mine;
+    p.voxel_num[f] = total < p.V ? total : p.V;
+  }
+  if (mine > 0) {   // warp-uniform
+    int32_t* ccell = p.creator_cell + wi0;
+    int run = excl;
+#pragma unroll
+    for (int r = 0; r < VF_ROUNDS; ++r) {
+      const bool cr = (creator >> r) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, cr);
+      if (cr) {
+        const int rank = run + __popc(bal & lt);
+        *vf_remote(cluster, map, cell[r], part) = ~rank;   // voxel id, stored negative so it never equals a point index
+        ccell[rank] = cell[r];                             // rank < number of points of the frame
+        if (rank == p.V && p.overflow == LV_OVERFLOW_BREAK)   // simplevis.py:48-49
+          for (int c = 0; c < CS; ++c) cluster.map_shared_rank(misc, c)[0] = lo + r * 32 + lane;
+      }
+      run += __popc(bal);
+    }
+  }
+  cluster.sync();
+  VF_MARK();
+
+  // ---- E: keys and the stable rank inside (warp, bin); cell[] now holds the key
+  const int cut = misc[0];
+  int* mycnt = cnt + warp * D;
+  int rnk[VF_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < VF_ROUNDS; ++r) {
+    int vid = 0x7fffffff;
+    if (cell[r] >= 0) vid = ~*vf_remote(cluster, map, cell[r], part);
+    cell[r] = (vid < p.V && lo + r * 32 + lane < cut) ? vid : -1;
+  }
+#pragma unroll
+  for (int r = 0; r < VF_ROUNDS; ++r) {
+    rnk[r] = 0;
+    if (lo + r * 32 >= hi) break;   // warp-uniform
+    const unsigned digit = cell[r] < 0 ? 0xffffffffu : ((unsigned)cell[r] >> p.low_bits);
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    const int leader = __ffs(peers) - 1;
+    int old = 0;
+    if (cell[r] >= 0 && lane == leader) {
+      old = mycnt[digit];
+      mycnt[digit] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rnk[r] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  VF_MARK();
+
+  // ---- F
+  for (int d = threadIdx.x; d < D; d += VF_THREADS) {
+    int acc = 0;
+    for (int w = 0; w < VF_WARPS; ++w) {
+      const int t = cnt[w * D + d];
+      cnt[w * D + d] = acc;
+      acc += t;
+    }
+    for (int c = 0; c < CS; ++c) cluster.map_shared_rank(ctot, c)[crank * D + d] = acc;
+  }
+  cluster.sync();
+  for (int d = threadIdx.x; d < D; d += VF_THREADS) {
+    int tot = 0;
+    for (int c = 0; c < CS; ++c) tot += ctot[c * D + d];
+    dbase[d] = tot;
+  }
+  __syncthreads();
+  if (warp == 0) {   // exclusive scan of the bin totals (D <= a few hundred)
+    int carry = 0;
+    for (int d0 = 0; d0 < D; d0 += 32) {
+      const int d = d0 + lane;
+      const int v = d < D ? dbase[d] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (d < D) dbase[d] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (crank == 0 && lane == 0) p.frame_kept[fl] = carry;
+  }
+  __syncthreads();
+  {
+    const int cb = __ldg(p.frame_chunk + f) - p.chunk_lo;
+    const int nch = __ldg(p.frame_chunk + f + 1) - __ldg(p.frame_chunk + f);
+    int32_t* tab = p.hist + (int64_t)cb * D;
+    for (int d = threadIdx.x; d < D; d += VF_THREADS) {
+      int below = dbase[d];
+      for (int c = 0; c < crank; ++c) below += ctot[c * D + d];
+      for (int w = 0; w < VF_WARPS; ++w) cnt[w * D + d] += below;
+      if (crank == 0 && nch > 0) tab[(int64_t)d * nch] = dbase[d];   // what K6 reads: first position of bin d
+    }
+  }
+  __syncthreads();
+  VF_MARK();
+
+  // ---- G: what K5 writes - the kept points grouped by bin, in point order
+#pragma unroll
+  for (int r = 0; r < VF_ROUNDS; ++r) {
+    if (cell[r] < 0) continue;
+    const int64_t pos = wi0 + mycnt[(unsigned)cell[r] >> p.low_bits] + rnk[r];
+    p.keys[pos] = (unsigned)cell[r];
+    p.vals[pos] = lo + r * 32 + lane;
+  }
+#ifdef VX_PROFILE
+  VF_MARK();
+  if (p.prof && threadIdx.x == 0 && crank == 0) {
+    for (int i = 0; i + 1 < nq; ++i) atomicAdd(p.prof + 8 + i, (unsigned long long)(tq[i + 1] - tq[i]));
+    atomicAdd(p.prof + 15, 1ull);
+  }
+#endif
 }
 
 // ---------------------------------------------------------------- K6: bins -> output rows
@@ -1003,16 +1247,40 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   p.row_div_m = (unsigned)(((1ull << 32) + (uint32_t)T - 1) / (uint32_t)T);
 #ifdef VX_PROFILE
   static unsigned long long* d_prof = nullptr;
-  if (!d_prof) { cudaMalloc(&d_prof, 64); cudaMemset(d_prof, 0, 64); }
+  if (!d_prof) { cudaMalloc(&d_prof, 128); cudaMemset(d_prof, 0, 128); }
   p.prof = d_prof;
   {
-    unsigned long long hp[4];
-    cudaMemcpy(hp, d_prof, 32, cudaMemcpyDeviceToHost);
+    unsigned long long hp[16];
+    cudaMemcpy(hp, d_prof, 128, cudaMemcpyDeviceToHost);
+    if (hp[15]) fprintf(stderr, "[vx_frame profile] clusters %llu  A %.0f  B %.0f  C %.0f  D %.0f  E %.0f  F %.0f  G %.0f clocks\n", hp[15],
+                        (double)hp[8] / hp[15], (double)hp[9] / hp[15], (double)hp[10] / hp[15], (double)hp[11] / hp[15],
+                        (double)hp[12] / hp[15], (double)hp[13] / hp[15], (double)hp[14] / hp[15]);
     if (hp[3]) fprintf(stderr, "[vx_bins profile] CTAs %llu  prologue %.0f  phase1 %.0f  phase2 %.0f clocks per CTA (thread 0)\n", hp[3],
                        (double)hp[0] / hp[3], (double)hp[1] / hp[3], (double)hp[2] / hp[3]);
-    cudaMemset(d_prof, 0, 64);
+    cudaMemset(d_prof, 0, 128);
   }
 #endif
+
+  // cluster-per-frame prologue (vx_frame_kernel): the smallest cluster whose shared memory holds the frame's map
+  int frame_cs = 0, frame_part = 0;
+  size_t frame_smem = 0;
+  int64_t max_frame_pts = 0;
+  for (int f = 0; f < n_frames; ++f)
+    if (h_frame_offsets[f + 1] - h_frame_offsets[f] > max_frame_pts) max_frame_pts = h_frame_offsets[f + 1] - h_frame_offsets[f];
+  if (h->vox_frame_kernel != 0 && n_bins <= 512) {
+    for (int cs = 1; cs <= VF_MAX_CS; cs *= 2) {
+      const int64_t part = lv_div_up(G, cs);
+      const size_t bytes = ((size_t)part + (size_t)(VF_WARPS + VF_MAX_CS + 1) * n_bins + VF_MAX_CS * VF_WARPS + 8) * 4;
+      if (bytes <= 226 * 1024 && max_frame_pts <= (int64_t)cs * VF_WARPS * VF_ROUNDS * 32) {
+        frame_cs = cs; frame_part = (int)part; frame_smem = bytes;
+        break;
+      }
+    }
+    if (frame_cs > 0) {
+      if (c4) LV_CHECK_CUDA(cudaFuncSetAttribute(vx_frame_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)frame_smem));
+      else LV_CHECK_CUDA(cudaFuncSetAttribute(vx_frame_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)frame_smem));
+    }
+  }
 
   int f0 = 0;
   while (f0 < n_frames) {
@@ -1023,7 +1291,7 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     const int chunk_lo = frame_chunk[f0], nchunks = frame_chunk[f1] - chunk_lo;
     p.f0 = f0; p.f1 = f1; p.chunk_lo = chunk_lo; p.pt_lo = pt_lo;
 
-    LV_CHECK(h->vox_map.ensure((size_t)nf * G * 4, stream, 0x7f));
+    if (frame_cs == 0) LV_CHECK(h->vox_map.ensure((size_t)nf * G * 4, stream, 0x7f));
     LV_CHECK(h->vox_cell.ensure((size_t)(npts + 1) * 4 * 2, stream));            // cell + key0
     LV_CHECK(h->vox_keys[0].ensure((size_t)(npts + 1) * 4, stream));
     LV_CHECK(h->vox_vals[0].ensure((size_t)(npts + 1) * 4, stream));
@@ -1042,20 +1310,40 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     p.frame_cut = h->vox_frame_state.as<int32_t>();
     p.frame_kept = p.frame_cut + nf;
 
-    if (nchunks > 0) {
-      if (c4) vx_cells_kernel<true><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
-      else vx_cells_kernel<false><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
+    if (frame_cs > 0) {
+      // small grid: K1-K5 of every frame inside one thread-block cluster, the dense map in distributed shared memory
+      cudaLaunchConfig_t lc;
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDim = dim3((unsigned)(nf * frame_cs));
+      lc.blockDim = dim3(VF_THREADS);
+      lc.dynamicSmemBytes = frame_smem;
+      lc.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)frame_cs;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      lc.attrs = at;
+      lc.numAttrs = 1;
+      if (c4) LV_CHECK_CUDA(cudaLaunchKernelEx(&lc, vx_frame_kernel<true>, p, frame_part));
+      else LV_CHECK_CUDA(cudaLaunchKernelEx(&lc, vx_frame_kernel<false>, p, frame_part));
       LV_LAUNCH_CHECK(h);
-      vx_assign_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p);
+    } else {
+      if (nchunks > 0) {
+        if (c4) vx_cells_kernel<true><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
+        else vx_cells_kernel<false><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
+        LV_LAUNCH_CHECK(h);
+        vx_assign_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p);
+        LV_LAUNCH_CHECK(h);
+        vx_keys_kernel<<<nchunks, VX_THREADS, smem_keys, stream>>>(p);
+        LV_LAUNCH_CHECK(h);
+      }
+      vx_scan_hist_kernel<<<nf, VX_THREADS, 0, stream>>>(p);
       LV_LAUNCH_CHECK(h);
-      vx_keys_kernel<<<nchunks, VX_THREADS, smem_keys, stream>>>(p);
-      LV_LAUNCH_CHECK(h);
-    }
-    vx_scan_hist_kernel<<<nf, VX_THREADS, 0, stream>>>(p);
-    LV_LAUNCH_CHECK(h);
-    if (nchunks > 0) {
-      vx_scatter_kernel<<<nchunks, VX_THREADS, smem_scatter, stream>>>(p);
-      LV_LAUNCH_CHECK(h);
+      if (nchunks > 0) {
+        vx_scatter_kernel<<<nchunks, VX_THREADS, smem_scatter, stream>>>(p);
+        LV_LAUNCH_CHECK(h);
+      }
     }
     {
       dim3 grid_b((unsigned)n_bins, (unsigned)nf);

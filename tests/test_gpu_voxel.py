@@ -262,3 +262,55 @@ def test_fused_mean_vfe_second_config(vg, vo, cloud11, cout):
         np.testing.assert_allclose(mean[at:at + k].cpu().numpy(), po.simple_voxel_mean(v, n, cout), rtol=1e-6, atol=1e-6)
         at += k
     assert at == mean.shape[0]
+
+
+@pytest.mark.parametrize("mode", ["continue", "break"])
+def test_cluster_frame_kernel_equals_the_five_kernel_prologue(vg, vo, mode):
+    """lv_set_option("vox_frame_kernel", 1): K1-K5 of a frame inside one thread-block cluster (dense map in
+    distributed shared memory).  Opt-in; must be bit-identical to the default path and to the oracle -
+    ragged frames, an empty frame, max_voxels hit (both overflow rules), five features per point."""
+    import torch
+    from lyft3d_b200 import _native as nat
+    h = nat.get_handle(0)
+    rng = np.random.default_rng(21)
+    sizes = [53146, 0, 1, 31, 20000, 65536, 40001]
+    frames = []
+    for i, n in enumerate(sizes):
+        base = synth.c5_frame(40 + i)
+        if n > base.shape[0]:
+            base = np.concatenate([base, synth.c5_frame(90 + i)])
+        frames.append(base[:n])
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    for T, V in ((60, 30000), (7, 3000)):
+        outs = []
+        for on in (0, 1):
+            h.set_option("vox_frame_kernel", on)
+            try:
+                outs.append(vg.voxelize_frames(pts, offs, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, T, V,
+                                               overflow=mode, zero_tail=True))
+            finally:
+                h.set_option("vox_frame_kernel", 0)
+        for a, b in zip(outs[0], outs[1]):
+            assert torch.equal(a, b)
+        vnum = outs[1][3].cpu().numpy()
+        for f in (0, 4, 6):
+            v, c, n = vo.points_to_voxel(frames[f], synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, T, V, overflow=mode)
+            k = int(vnum[f])
+            assert k == v.shape[0]
+            assert np.array_equal(outs[1][1][f, :k].cpu().numpy(), c)
+            assert np.array_equal(outs[1][2][f, :k].cpu().numpy(), n)
+            assert np.array_equal(outs[1][0][f, :k].cpu().numpy().view(np.uint32), v.view(np.uint32))
+    assert rng is not None
+    # five features per point (the non-float4 load path)
+    p5 = torch.cat([pts[:53146], torch.rand((53146, 1), device="cuda")], dim=1).contiguous()
+    o5 = np.array([0, 53146], dtype=np.int64)
+    res = []
+    for on in (0, 1):
+        h.set_option("vox_frame_kernel", on)
+        try:
+            res.append(vg.voxelize_frames(p5, o5, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000, overflow=mode))
+        finally:
+            h.set_option("vox_frame_kernel", 0)
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
