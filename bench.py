@@ -185,6 +185,24 @@ def time_other_configs(dev, reps=10):
                                             n_frames=1, want=("u8", "chw"), map_u8=maps, out=res))
     out["C4 BEV 1024x1024x3, 20 sweeps with 4x4, u8 + (6,1024,1024) CHW with map"] = {
         "points": n, "ms": round(ms, 4), "points_per_s": round(n / (ms * 1e-3))}
+    # the drop-in call of a DataLoader worker (preprocess.py:299-317): host numpy in, host numpy out, wall clock
+    from oracle import voxel_oracle
+    sweep = synth.fixture_points_nx4()
+    gen = vg.VoxelGeneratorV2(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, max_voxels=30000)
+    for _ in range(3):
+        gen.generate(sweep, 30000)
+    t0 = _time.perf_counter()
+    for _ in range(reps):
+        gen.generate(sweep, 30000)
+    gen_ms = (_time.perf_counter() - t0) / reps * 1e3
+    ora = voxel_oracle.VoxelOracle(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)
+    ora.generate(sweep)
+    t0 = _time.perf_counter()
+    for _ in range(3):
+        ora.generate(sweep)
+    ora_ms = (_time.perf_counter() - t0) / 3 * 1e3
+    out["C3 VoxelGeneratorV2.generate on the bundled sweep, drop-in call with host buffers"] = {
+        "points": int(sweep.shape[0]), "ms": round(gen_ms, 4), "cpu_port_ms": round(ora_ms, 3)}
     # block-filtering voxelizer (all.fhd.config) on the same cloud; target raster of 128 frames
     fhd_vs, fhd_rg = (0.05, 0.05, 0.2), (-50, -50, -5, 50, 50, 3)
     ms = timed(lambda: vg.voxelize_frames(cloud, offs, fhd_vs, fhd_rg, 5, 60000, zero_tail=False,

@@ -293,6 +293,17 @@ int lv_voxelize_filtered_host(lv_handle* h, const lv_voxel_config* cfg, const lv
                               float* h_voxels, int32_t* h_coords, int32_t* h_num_points,
                               int32_t* h_voxel_num);
 
+/* The host-buffer call in two phases, for callers that want arrays of exactly voxel_num rows
+ * (VoxelGeneratorV2.generate slices to voxel_num anyway, second/second/data/preprocess.py:305-310):
+ * _begin copies the points in, runs the kernels (block filter when flt != NULL) and returns the voxel
+ * count of every frame; the results stay in the handle's staging buffers until the next *_host call.
+ * _fetch copies the first `rows` rows of one frame into caller arrays (rows, T, C) / (rows, 3) / (rows). */
+int lv_voxelize_host_begin(lv_handle* h, const lv_voxel_config* cfg, const lv_block_filter* flt,
+                           const float* h_points, int32_t n_frames, const int64_t* h_frame_offsets,
+                           int32_t* h_voxel_num);
+int lv_voxelize_host_fetch(lv_handle* h, int32_t frame, int32_t rows, float* h_voxels,
+                           int32_t* h_coords, int32_t* h_num_points);
+
 /* ------------------------------------------------------------------ PointPillars
  *
  * lv_pillar_decorate replaces the decoration part of

@@ -97,6 +97,9 @@ SIGNATURES = {
                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lv_voxelize_filtered_host": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), ctypes.POINTER(BlockFilter), _vp,
                                                  _i32, _vp, _vp, _vp, _vp, _vp]),
+    "lv_voxelize_host_begin": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), ctypes.POINTER(BlockFilter), _vp, _i32,
+                                              _vp, _vp]),
+    "lv_voxelize_host_fetch": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "lv_pillar_out_channels": (ctypes.c_int, [_i32, _i32, _i32]),
     "lv_pillar_decorate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32,
                                           _i32, _i32, _vp, _vp]),

@@ -94,6 +94,8 @@ struct lv_handle {
   lv_buffer vox_row_base;
   lv_mirror vox_frame_offsets, vox_chunk_table, vox_chunk_frame;
   lv_buffer vox_stage_points, vox_stage_out[4];
+  int32_t vox_host_frames = 0;        // frames held by the staging buffers since the last lv_voxelize_host_begin
+  lv_voxel_config vox_host_cfg;       // its configuration
   lv_buffer flt_ranges, flt_dst, flt_tmp[4];   // block filter: z ranges per block, destination rows, unfiltered voxels
 
   // pillar

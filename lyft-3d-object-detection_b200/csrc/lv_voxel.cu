@@ -1417,19 +1417,25 @@ extern "C" int lv_pillarize_pfn_concat(lv_handle* h, const lv_voxel_config* cfg,
                 capacity_rows, d_voxel_offsets, &d, d_features, &c, stream);
 }
 
-static int vx_host_run(lv_handle* h, const lv_voxel_config* cfg, const lv_block_filter* flt, const float* h_points,
-                       int32_t n_frames, const int64_t* h_frame_offsets, float* h_voxels, int32_t* h_coords,
-                       int32_t* h_num_points, int32_t* h_voxel_num) {
+// Host-buffer entry points in two phases: _begin copies the points in, runs the kernels and returns the voxel counts
+// (results stay in the handle's staging buffers); _fetch copies `rows` rows of one frame into caller arrays of exactly
+// that size.  VoxelGeneratorV2.generate uses them so that it never allocates, touches or transfers the padded
+// (max_voxels, T, C) array (preprocess.py:305-310 slices to voxel_num anyway).
+extern "C" int lv_voxelize_host_begin(lv_handle* h, const lv_voxel_config* cfg, const lv_block_filter* flt,
+                                      const float* h_points, int32_t n_frames, const int64_t* h_frame_offsets,
+                                      int32_t* h_voxel_num) {
   LV_REQUIRE(h != nullptr, "lv_voxelize_host: null handle");
   LV_REQUIRE(cfg && h_frame_offsets && n_frames >= 0, "lv_voxelize_host: bad arguments");
   LV_REQUIRE(cfg->num_features >= 3 && cfg->max_points > 0 && cfg->max_voxels > 0, "lv_voxelize_host: bad config");
+  h->vox_host_frames = 0;
   if (n_frames == 0) return LV_OK;
-  LV_REQUIRE(h_voxels && h_coords && h_num_points && h_voxel_num, "lv_voxelize_host: null output");
+  LV_REQUIRE(h_voxel_num != nullptr, "lv_voxelize_host: null output");
   LV_CHECK_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = h->own_stream;
   const int64_t n_total = h_frame_offsets[n_frames];
   const size_t V = cfg->max_voxels, T = cfg->max_points, C = cfg->num_features, F = n_frames;
   const size_t pt_bytes = (size_t)n_total * C * 4;
+  LV_REQUIRE(pt_bytes == 0 || h_points, "lv_voxelize_host: null points");
   LV_CHECK(h->vox_stage_points.ensure(pt_bytes, st));
   LV_CHECK(h->vox_stage_out[0].ensure(F * V * T * C * 4, st));
   LV_CHECK(h->vox_stage_out[1].ensure(F * V * 3 * 4, st));
@@ -1444,20 +1450,45 @@ static int vx_host_run(lv_handle* h, const lv_voxel_config* cfg, const lv_block_
     LV_CHECK(lv_voxelize(h, cfg, h->vox_stage_points.as<float>(), n_frames, h_frame_offsets, h->vox_stage_out[0].as<float>(),
                          h->vox_stage_out[1].as<int32_t>(), h->vox_stage_out[2].as<int32_t>(),
                          h->vox_stage_out[3].as<int32_t>(), st));
-  // voxel_num first: with zero_tail == 0 only the live rows are brought back
   LV_CHECK_CUDA(cudaMemcpyAsync(h_voxel_num, h->vox_stage_out[3].ptr, F * 4, cudaMemcpyDeviceToHost, st));
   LV_CHECK_CUDA(cudaStreamSynchronize(st));
-  for (size_t f = 0; f < F; ++f) {
-    const size_t rows = cfg->zero_tail ? V : (size_t)h_voxel_num[f];
-    if (rows == 0) continue;
-    LV_CHECK_CUDA(cudaMemcpyAsync(h_voxels + f * V * T * C, h->vox_stage_out[0].as<float>() + f * V * T * C,
-                                  rows * T * C * 4, cudaMemcpyDeviceToHost, st));
-    LV_CHECK_CUDA(cudaMemcpyAsync(h_coords + f * V * 3, h->vox_stage_out[1].as<int32_t>() + f * V * 3, rows * 3 * 4,
-                                  cudaMemcpyDeviceToHost, st));
-    LV_CHECK_CUDA(cudaMemcpyAsync(h_num_points + f * V, h->vox_stage_out[2].as<int32_t>() + f * V, rows * 4,
-                                  cudaMemcpyDeviceToHost, st));
-  }
+  h->vox_host_frames = n_frames;
+  h->vox_host_cfg = *cfg;
+  return LV_OK;
+}
+
+extern "C" int lv_voxelize_host_fetch(lv_handle* h, int32_t frame, int32_t rows, float* h_voxels, int32_t* h_coords,
+                                      int32_t* h_num_points) {
+  LV_REQUIRE(h != nullptr, "lv_voxelize_host_fetch: null handle");
+  LV_REQUIRE(frame >= 0 && frame < h->vox_host_frames, "lv_voxelize_host_fetch: frame %d is not part of the last "
+             "lv_voxelize_host_begin (%d frames)", frame, h->vox_host_frames);
+  const size_t V = h->vox_host_cfg.max_voxels, T = h->vox_host_cfg.max_points, C = h->vox_host_cfg.num_features, f = frame;
+  LV_REQUIRE(rows >= 0 && (size_t)rows <= V, "lv_voxelize_host_fetch: rows %d outside [0, max_voxels]", rows);
+  if (rows == 0) return LV_OK;
+  LV_REQUIRE(h_voxels && h_coords && h_num_points, "lv_voxelize_host_fetch: null output");
+  LV_CHECK_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = h->own_stream;
+  LV_CHECK_CUDA(cudaMemcpyAsync(h_voxels, h->vox_stage_out[0].as<float>() + f * V * T * C, (size_t)rows * T * C * 4,
+                                cudaMemcpyDeviceToHost, st));
+  LV_CHECK_CUDA(cudaMemcpyAsync(h_coords, h->vox_stage_out[1].as<int32_t>() + f * V * 3, (size_t)rows * 3 * 4,
+                                cudaMemcpyDeviceToHost, st));
+  LV_CHECK_CUDA(cudaMemcpyAsync(h_num_points, h->vox_stage_out[2].as<int32_t>() + f * V, (size_t)rows * 4,
+                                cudaMemcpyDeviceToHost, st));
   LV_CHECK_CUDA(cudaStreamSynchronize(st));
+  return LV_OK;
+}
+
+static int vx_host_run(lv_handle* h, const lv_voxel_config* cfg, const lv_block_filter* flt, const float* h_points,
+                       int32_t n_frames, const int64_t* h_frame_offsets, float* h_voxels, int32_t* h_coords,
+                       int32_t* h_num_points, int32_t* h_voxel_num) {
+  LV_CHECK(lv_voxelize_host_begin(h, cfg, flt, h_points, n_frames, h_frame_offsets, h_voxel_num));
+  if (n_frames == 0) return LV_OK;
+  LV_REQUIRE(h_voxels && h_coords && h_num_points, "lv_voxelize_host: null output");
+  const size_t V = cfg->max_voxels, T = cfg->max_points, C = cfg->num_features;
+  // with zero_tail == 0 only the live rows are brought back
+  for (int32_t f = 0; f < n_frames; ++f)
+    LV_CHECK(lv_voxelize_host_fetch(h, f, cfg->zero_tail ? (int32_t)V : h_voxel_num[f], h_voxels + (size_t)f * V * T * C,
+                                    h_coords + (size_t)f * V * 3, h_num_points + (size_t)f * V));
   return LV_OK;
 }
 

@@ -116,6 +116,35 @@ def voxelize_frames(points, frame_offsets, voxel_size, coors_range, max_points, 
     return voxels, coords, num, vnum
 
 
+def voxelize_host_single(points, voxel_size, coors_range, max_points, max_voxels, overflow="continue",
+                         padded=False, block_filter=None, handle=None):
+    """One cloud, host numpy in and out, through lv_voxelize_host_begin / _fetch: the arrays that come
+    back have exactly voxel_num rows (``padded=False``, what ``generate`` returns) or max_voxels rows of which
+    only the first voxel_num crossed the bus (``padded=True``, the generate_multi_gpu layout: the rest is
+    the zero fill of a fresh allocation).  Returns (voxels, coordinates, num_points_per_voxel, voxel_num)."""
+    lib = nat.load()
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    if pts.ndim != 2:
+        raise ValueError("points must be (N, C)")
+    C = pts.shape[1]
+    V, T = int(max_voxels), int(max_points)
+    cfg = _make_config(voxel_size, coors_range, T, V, C, overflow, False)
+    offs = np.array([0, pts.shape[0]], dtype=np.int64)
+    vnum = np.zeros((1,), dtype=np.int32)
+    h = handle or nat.get_handle()
+    flt = _make_filter(block_filter) if block_filter is not None else None
+    nat.check(lib.lv_voxelize_host_begin(h.ptr, ctypes.byref(cfg), ctypes.byref(flt) if flt is not None else None,
+                                         pts.ctypes.data, 1, offs.ctypes.data, vnum.ctypes.data))
+    k = int(vnum[0])
+    rows = V if padded else k
+    alloc = np.zeros if padded else np.empty
+    voxels = alloc((rows, T, C), dtype=np.float32)
+    coords = alloc((rows, 3), dtype=np.int32)
+    num = alloc((rows,), dtype=np.int32)
+    nat.check(lib.lv_voxelize_host_fetch(h.ptr, 0, k, voxels.ctypes.data, coords.ctypes.data, num.ctypes.data))
+    return voxels, coords, num, k
+
+
 class VoxelGeneratorV2:
     """spconv.utils.VoxelGeneratorV2-compatible generator (see module docstring)."""
 
@@ -151,6 +180,9 @@ class VoxelGeneratorV2:
     def _run(self, points, max_voxels, padded):
         mv = self._max_voxels if max_voxels is None else int(max_voxels)
         n = points.shape[0]
+        if not _is_cuda_tensor(points):
+            return voxelize_host_single(points, self._voxel_size, self._point_cloud_range, self._max_num_points, mv,
+                                        overflow=self._overflow, padded=padded, block_filter=self._block_filter)
         voxels, coords, num, vnum = voxelize_frames(
             points, np.array([0, n], dtype=np.int64), self._voxel_size, self._point_cloud_range,
             self._max_num_points, mv, overflow=self._overflow, zero_tail=padded,
