@@ -105,38 +105,46 @@ __global__ void __launch_bounds__(VF_THREADS) vf_mask_kernel(FilterParams p) {
   }
 }
 
-// one CTA of 1024 threads per frame: flags -> destination rows (stable), kept count
+// one CTA of 1024 threads per frame: flags -> destination rows (stable), kept count.  Warp w owns a contiguous
+// span of voxels and walks it in coalesced rounds of 32 (ballot + popc), so one scan of the 32 warp totals orders
+// everything.
 __global__ void __launch_bounds__(1024) vf_scan_kernel(FilterParams p) {
   __shared__ int s_warp[32];
-  __shared__ int s_base;
   const int f = p.f0 + blockIdx.x;
   int vnum = p.voxel_num[f];
   vnum = vnum < 0 ? 0 : (vnum > p.V ? p.V : vnum);
   const int64_t base = (int64_t)f * p.V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_base = 0;
+  const int span = (((vnum + 31) >> 5) + 31) & ~31;          // voxels per warp, a multiple of 32
+  const int lo = min(warp * span, vnum), hi = min(lo + span, vnum);
+  int mine = 0;
+#pragma unroll 4
+  for (int v0 = lo; v0 < hi; v0 += 32) {
+    const int v = v0 + lane;
+    mine += __popc(__ballot_sync(0xffffffffu, v < hi && p.dst[base + v] != 0));
+  }
+  if (lane == 0) s_warp[warp] = mine;
   __syncthreads();
-  for (int v0 = 0; v0 < vnum; v0 += 1024) {
-    const int v = v0 + threadIdx.x;
-    const int keep = v < vnum ? p.dst[base + v] : 0;
+  int run = 0, total = 0;
+  for (int w = 0; w < 32; ++w) {
+    const int t = s_warp[w];
+    if (w < warp) run += t;
+    total += t;
+  }
+#pragma unroll 4
+  for (int v0 = lo; v0 < hi; v0 += 32) {
+    const int v = v0 + lane;
+    const int keep = (v < hi && p.dst[base + v] != 0) ? 1 : 0;
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    int before = 0;
-    for (int w = 0; w < warp; ++w) before += s_warp[w];
-    const int run = s_base;
-    if (v < vnum) {
-      const int d = keep ? run + before + __popc(bal & ((1u << lane) - 1u)) : -1;
-      p.dst[base + v] = d;
+    if (v < hi) {
+      p.dst[base + v] = keep ? run + __popc(bal & ((1u << lane) - 1u)) : -1;
       if (p.out_mask) p.out_mask[base + v] = keep;
     }
-    __syncthreads();
-    if (threadIdx.x == 1023) s_base = run + before + __popc(bal);
-    __syncthreads();
+    run += __popc(bal);
   }
   if (p.out_mask)
     for (int v = vnum + threadIdx.x; v < p.V; v += 1024) p.out_mask[base + v] = 0;
-  if (threadIdx.x == 0) p.out_voxel_num[f] = s_base;
+  if (threadIdx.x == 0) p.out_voxel_num[f] = total;
 }
 
 // grid (row blocks, frames): a warp per source row
