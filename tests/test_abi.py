@@ -69,10 +69,20 @@ def test_no_cpu_fallback(lib):
     rc = lib.lv_create(0, ctypes.byref(h))
     assert rc == nat.LV_E_NODEVICE and not h.value
     assert b"no CPU fallback" in lib.lv_last_error(None)
-    from lyft3d_b200 import bev
+    from lyft3d_b200 import bev, voxel_generator as vg
     pts = np.zeros((4, 10), np.float32)
     with pytest.raises(nat.LyftVoxelError):
         bev.create_voxel_pointcloud(pts, (8, 8, 3), (1, 1, 1), 0)
+    # every drop-in fails the same way: generate (plain and block-filtering), the target raster
+    gen = vg.VoxelGeneratorV2([0.25, 0.25, 8], [-50, -50, -5, 50, 50, 3], 60, max_voxels=100)
+    with pytest.raises(nat.LyftVoxelError):
+        gen.generate(np.zeros((10, 4), np.float32))
+    flt = vg.VoxelGeneratorV2([0.25, 0.25, 8], [-50, -50, -5, 50, 50, 3], 5, max_voxels=100, block_filtering=True,
+                              block_factor=1, block_size=8, height_threshold=0.2)
+    with pytest.raises(nat.LyftVoxelError):
+        flt.generate_multi_gpu(np.zeros((10, 4), np.float32))
+    with pytest.raises(nat.LyftVoxelError):
+        bev.rasterize_targets(np.zeros((1, 3, 4)), np.ones(1, np.int32), np.array([0, 1]), (8, 8, 3), (1, 1, 1))
 
 
 def test_product_does_not_import_oracle():
