@@ -1312,8 +1312,7 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
 
     if (frame_cs > 0) {
       // small grid: K1-K5 of every frame inside one thread-block cluster, the dense map in distributed shared memory
-      cudaLaunchConfig_t lc;
-      memset(&lc, 0, sizeof(lc));
+      cudaLaunchConfig_t lc = {};
       lc.gridDim = dim3((unsigned)(nf * frame_cs));
       lc.blockDim = dim3(VF_THREADS);
       lc.dynamicSmemBytes = frame_smem;
