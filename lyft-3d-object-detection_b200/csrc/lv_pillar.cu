@@ -515,15 +515,16 @@ static int pillar_scatter_run(lv_handle* h, const float* d_feats, const int32_t*
   // canvas_variant: 0 = auto (128-bit gathers when the shape allows), 1 = always the row-per-step kernel (A/B)
   const bool quad = vec && h->canvas_variant != 1 && ncell % SC_TILE == 0 && channels % 32 == 0 &&
                     (reinterpret_cast<uintptr_t>(d_feats) & 15) == 0;
+  // every argument check sits in front of the first launch: a failing call must leave the cell->pillar map all -1
+  LV_REQUIRE(n_pillars * (int64_t)channels < (1ll << 32), "lv_pillar_scatter: %lld pillars x %d channels exceed 2^32 features",
+             (long long)n_pillars, channels);
+  const int64_t grid = (int64_t)tiles * batch_size;
+  LV_REQUIRE(grid < (1ll << 31), "lv_pillar_scatter: canvas too large");
   if (n_pillars > 0) {
     pillar_index_kernel<<<(unsigned)lv_div_up(n_pillars, 256), 256, 0, stream>>>(d_coords, n_pillars, d_n_pillars,
                                                                                batch_size, ny, nx, h->pil_map.as<int32_t>());
     LV_LAUNCH_CHECK(h);
   }
-  LV_REQUIRE(n_pillars * (int64_t)channels < (1ll << 32), "lv_pillar_scatter: %lld pillars x %d channels exceed 2^32 features",
-             (long long)n_pillars, channels);
-  const int64_t grid = (int64_t)tiles * batch_size;
-  LV_REQUIRE(grid < (1ll << 31), "lv_pillar_scatter: canvas too large");
   if (quad)
     pillar_canvas_q_kernel<true, 6><<<(unsigned)grid, SC_THREADS, 0, stream>>>(d_feats, h->pil_map.as<int32_t>(), channels,
                                                                              ncell, tiles, d_canvas);

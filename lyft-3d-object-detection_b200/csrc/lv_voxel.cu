@@ -928,8 +928,9 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : VX_BINS_M
       if (n1 > p.T) n1 = p.T;
       const int* sl = slot_tab + v * p.T;
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (two && n0 <= 16 && n1 <= 16 && p.T > 16) {
-        // two small pillars (the common case: 5.4 points per pillar on a Lyft sweep) share the warp
+      if (two && n0 <= 16 && n1 <= 16 && p.T >= 32) {
+        // two small pillars (the common case: 5.4 points per pillar on a Lyft sweep) share the warp.
+        // T >= 32: the second half's stage starts 16 slots into the warp's T-slot stage and holds up to 16 more
         const int hi = lane >> 4, sub = lane & 15;
         const int nm = hi ? n1 : n0;
         float4 a = z4;

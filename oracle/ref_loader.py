@@ -170,3 +170,48 @@ def run_bev_draw_boxes(im, voxel_size, corners, class_ids, classes, z_offset=0.0
     boxes = [_Box(np.asarray(c, dtype=np.float64), classes[int(k)]) for c, k in zip(corners, class_ids)]
     ns["draw_boxes"](im, voxel_size, boxes=boxes, classes=classes, z_offset=z_offset)
     return im
+
+
+def load_bev_closures():
+    """The reference's own BEV closures (generating-dataset/generating_train_bev.py:47-104), nested in
+    ``main``: their source lines are read from the reference file, dedented and executed
+    unchanged; only ``np.int0`` (removed in numpy 2) is aliased to ``np.intp`` - the same C cast.
+    Returns a dict name -> function."""
+    import textwrap
+    import types
+
+    import numpy as np
+    path = os.path.join(REF, "generating-dataset", "generating_train_bev.py")
+    with open(path) as f:
+        lines = f.readlines()
+
+    def block(name):
+        start = next(i for i, l in enumerate(lines) if l.lstrip().startswith("def %s(" % name))
+        indent = len(lines[start]) - len(lines[start].lstrip())
+        end = start + 1
+        while end < len(lines) and (not lines[end].strip() or len(lines[end]) - len(lines[end].lstrip()) > indent):
+            end += 1
+        return textwrap.dedent("".join(lines[start:end]))
+
+    npx = types.SimpleNamespace(**{k: getattr(np, k) for k in dir(np) if not k.startswith("__")})
+    npx.int0 = np.intp
+    ns = {"np": npx}
+    names = ("create_transformation_matrix_to_voxel_space", "transform_points", "car_to_voxel_coords",
+             "create_voxel_pointcloud", "normalize_voxel_intensities")
+    for name in names:
+        exec(compile(block(name), path, "exec"), ns)
+    return {n: ns[n] for n in names}
+
+
+def run_bev_closures(points, shape, voxel_size, z_offset):
+    """points (3|4, N) float32 -> (raw counts f32, normalised f32, u8 image) exactly as
+    prepare_training_data_for_scene computes them (generating_train_bev.py:210-213): the reference's
+    create_voxel_pointcloud, normalize_voxel_intensities and the ``np.round(bev*255).astype(np.uint8)``
+    statement."""
+    import numpy as np
+    fn = load_bev_closures()
+    with np.errstate(invalid="ignore"):
+        raw = fn["create_voxel_pointcloud"](points, shape, voxel_size=voxel_size, z_offset=z_offset)
+    bev = fn["normalize_voxel_intensities"](raw)
+    bev_im = np.round(bev * 255).astype(np.uint8)
+    return raw, bev, bev_im
