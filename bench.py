@@ -376,7 +376,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    launches0 = eng.h.launches()
+    launches0 = eng.h.launches() + (pipe_eng.launches() if pipe_eng is not None else 0)
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_start.record()
@@ -390,7 +390,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches = eng.h.launches() - launches0
+    launches = eng.h.launches() + (pipe_eng.launches() if pipe_eng is not None else 0) - launches0
     ms_total = t_start.elapsed_time(t_end)
     clocks = sampler.stop() if sampler else None
 
@@ -506,9 +506,10 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                         "d2h_bytes_per_step": pipe.d2h_bytes, "rank0_numa_node": numa_node,
-                        "note": "HostPipeline: pinned host points -> device -> both paths -> BEV u8 + voxel_num "
-                                "back in pinned host memory every step (copies overlap the next step's kernels); "
-                                "the canvas stays on the device (its consumer is the RPN, voxelnet.py:336)"}}
+                        "note": "HostPipeline: pinned host points -> device -> both paths -> the BEV images as PNG "
+                                "FILES (generating_train_bev.py:215; lv_png_encode writes them into mapped pinned "
+                                "host memory) + file sizes + voxel_num on the host every step, no host sync inside "
+                                "the loop; the canvas stays on the device (its consumer is the RPN, voxelnet.py:336)"}}
         if world == 1 and not args.no_other_configs:
             line["other_configs"] = time_other_configs(dev)
         if world == 1 and not args.no_cpu_baseline:

@@ -62,7 +62,9 @@ int64_t lv_workspace_bytes(lv_handle* h);
 /* Number of kernels this handle has launched since creation (bench.py's
  * gpu_launches claim is read from here). */
 int64_t lv_launch_count(lv_handle* h);
-/* Pinned host memory for callers of the *_host entry points. */
+/* Pinned host memory for callers of the *_host entry points.  The allocation is MAPPED and portable: under
+ * unified addressing the same pointer is valid in kernels, which is what lets lv_png_encode write its
+ * files straight into host memory. */
 int lv_host_alloc(size_t bytes, void** out);
 int lv_host_free(void* p);
 /* Tuning knobs (0 = library default). */
@@ -134,6 +136,28 @@ int lv_draw_boxes(lv_handle* h, const double* d_corners, const int32_t* d_colors
 int lv_draw_boxes_host(lv_handle* h, const double* h_corners, const int32_t* h_colors,
                        int32_t n_frames, const int64_t* h_box_offsets, const int32_t shape[3],
                        const double voxel_size[3], double z_offset, uint8_t* h_target);
+
+/* PNG encoding on the device: cv2.imwrite(path, image) of generating-dataset/generating_train_bev.py:215
+ * ("{token}_input.png", (H,W,3) uint8), :224 ("{token}_target.png", (H,W) uint8) and :229, for images that
+ * already live in HBM - an encoded sparse BEV image is ~16x smaller than the dense array that would cross
+ * PCIe otherwise.  PNG is lossless; the contract is decode-exactness under cv2.imread(..., IMREAD_UNCHANGED)
+ * (deeplab_v3_baseline/dataset/dataset.py:83-90), and the byte stream is the one stated by
+ * oracle/png_oracle.py: filter type 0, ONE fixed-Huffman deflate block (run-length matches at distance 1),
+ * Adler-32, CRC-32, a single IDAT.
+ *   d_images  uint8 (n_frames, height, width, channels)  channels 1 (grey) or 3; width*channels < 4096
+ *   swap_rb   non-zero: a 3-channel image is in OpenCV's B,G,R order and is written R,G,B (= cv2.imwrite)
+ *   out       frame f's file starts at out + f*out_stride.  DEVICE memory or MAPPED PINNED HOST memory
+ *             (lv_host_alloc): in the second case the file bytes cross PCIe as they are produced and
+ *             nothing else is transferred.  Bytes of a slot beyond the file size are not written.
+ *   sizes     int32 (n_frames), device or mapped host: file size of frame f, or MINUS the size it needs
+ *             when out_stride is too small (lv_png_max_bytes is always enough). */
+int64_t lv_png_max_bytes(int32_t height, int32_t width, int32_t channels);
+int lv_png_encode(lv_handle* h, const uint8_t* d_images, int32_t n_frames, int32_t height, int32_t width,
+                  int32_t channels, int32_t swap_rb, uint8_t* out, int64_t out_stride, int32_t* sizes,
+                  lv_stream stream);
+/* Host images in, host files out (a caller that holds numpy images: the cv2.imwrite / cv2.imencode call). */
+int lv_png_encode_host(lv_handle* h, const uint8_t* h_images, int32_t n_frames, int32_t height, int32_t width,
+                       int32_t channels, int32_t swap_rb, uint8_t* h_out, int64_t out_stride, int32_t* h_sizes);
 
 /* normalize_voxel_intensities alone (generating_train_bev.py:103-104) on a
  * device array of n float32: out = clip(in / max_intensity, 0, 1). */

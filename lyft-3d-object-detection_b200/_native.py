@@ -78,6 +78,9 @@ SIGNATURES = {
                                              _vp, _vp, _vp, _vp, _vp]),
     "lv_draw_boxes": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _f64, _vp, _vp]),
     "lv_draw_boxes_host": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _f64, _vp]),
+    "lv_png_max_bytes": (_i64, [_i32, _i32, _i32]),
+    "lv_png_encode": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "lv_png_encode_host": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "lv_bev_normalize": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp, _vp]),
     "lv_transform_points": (ctypes.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "lv_ingest_sweeps": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32, _vp, _vp]),

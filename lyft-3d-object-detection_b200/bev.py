@@ -227,6 +227,87 @@ def quantize_u8(points, shape, voxel_size=(0.5, 0.5, 1), z_offset=0, max_intensi
     return res["u8"][0]
 
 
+def png_slot_bytes(height, width, channels):
+    """Slot size that always holds the PNG of a (height, width, channels) uint8 image."""
+    n = int(nat.load().lv_png_max_bytes(int(height), int(width), int(channels)))
+    if n <= 0:
+        raise Exception("PNG images are (H,W) or (H,W,3) uint8")
+    return (n + 255) // 256 * 256
+
+
+def encode_png_frames(images, out=None, sizes=None, stride=None, swap_rb=True, handle=None):
+    """Device-side PNG encoding of a batch: images (F,H,W) or (F,H,W,3) uint8 CUDA tensor ->
+    (out, sizes): frame f's file is out[f, :sizes[f]].  `out` (F, stride) uint8 and `sizes` (F) int32 may be
+    CUDA tensors or tensors over mapped pinned host memory (engine.MappedBuffer): the kernels then write the
+    files straight into host memory.  Asynchronous on torch's current stream.
+    cv2.imwrite of generating_train_bev.py:215,224 (B,G,R arrays are written R,G,B: swap_rb)."""
+    import torch
+    lib = nat.load()
+    if not (_is_cuda_tensor(images) and images.dtype == torch.uint8 and images.dim() in (3, 4)):
+        raise Exception("images must be a (F,H,W) or (F,H,W,3) uint8 CUDA tensor")
+    images = images.contiguous()
+    F, H, W = int(images.shape[0]), int(images.shape[1]), int(images.shape[2])
+    ch = 1 if images.dim() == 3 else int(images.shape[3])
+    if ch not in (1, 3):
+        raise Exception("PNG images have 1 or 3 channels, got %d" % ch)
+    if stride is None:
+        stride = int(out.shape[1]) if out is not None else png_slot_bytes(H, W, ch)
+    if out is None:
+        out = torch.empty((F, stride), dtype=torch.uint8, device=images.device)
+    if sizes is None:
+        sizes = torch.empty((F,), dtype=torch.int32, device=images.device)
+    h = handle or nat.get_handle(images.device.index)
+    with torch.cuda.device(images.device):
+        nat.check(lib.lv_png_encode(h.ptr, images.data_ptr(), F, H, W, ch, int(bool(swap_rb)), out.data_ptr(), int(stride),
+                                    sizes.data_ptr(), nat.current_stream_ptr(images.device)))
+    return out, sizes
+
+
+def imencode_png(image):
+    """cv2.imencode('.png', image)[1].tobytes() for a uint8 (H,W) / (H,W,3) array (numpy or CUDA tensor), or a
+    list of files for a batch (F,H,W,3) / a CUDA (F,H,W) tensor given as `image[None]`.  Lossless: decoding with
+    cv2.imread / cv2.imdecode returns the array."""
+    import torch
+    single = False
+    if _is_cuda_tensor(image):
+        t = image
+        if t.dim() == 2 or (t.dim() == 3 and t.shape[2] == 3):
+            t, single = t[None], True
+        out, sizes = encode_png_frames(t)
+        sizes = sizes.cpu().numpy()
+        out = out.cpu().numpy()
+    else:
+        a = np.ascontiguousarray(image)
+        if a.dtype != np.uint8:
+            raise Exception("PNG images must be uint8, got %s" % a.dtype)
+        if a.ndim == 2 or (a.ndim == 3 and a.shape[2] in (1, 3)):
+            a, single = a[None], True
+        if a.ndim == 4 and a.shape[3] == 1:
+            a = a[..., 0]
+        if a.ndim not in (3, 4) or (a.ndim == 4 and a.shape[3] != 3):
+            raise Exception("PNG images are (H,W), (H,W,3) or a batch of them")
+        F, H, W = a.shape[:3]
+        ch = 1 if a.ndim == 3 else 3
+        lib = nat.load()
+        stride = png_slot_bytes(H, W, ch)
+        out = np.empty((F, stride), np.uint8)
+        sizes = np.empty((F,), np.int32)
+        nat.check(lib.lv_png_encode_host(nat.get_handle().ptr, a.ctypes.data, F, H, W, ch, 1, out.ctypes.data, stride,
+                                         sizes.ctypes.data))
+    files = [out[f, :int(sizes[f])].tobytes() for f in range(len(sizes))]
+    return files[0] if single else files
+
+
+def imwrite(path, image):
+    """cv2.imwrite(path, image) for 8-bit PNG files (generating_train_bev.py:215,224,229)."""
+    if not str(path).lower().endswith(".png"):
+        raise Exception("imwrite: only .png is produced, got %r" % (path,))
+    data = imencode_png(image)
+    with open(path, "wb") as f:
+        f.write(data)
+    return True
+
+
 def rasterize_targets(corners, colors, box_offsets, shape, voxel_size, z_offset=0.0, handle=None):
     """Batched target rasterisation (lv_draw_boxes): frame f paints boxes
     [box_offsets[f], box_offsets[f+1]) in order, later over earlier.

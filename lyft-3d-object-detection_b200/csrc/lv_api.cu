@@ -134,7 +134,7 @@ int lv_host_alloc(size_t bytes, void** out) {
     return LV_E_INVALID;
   }
   *out = nullptr;
-  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable);
   if (e != cudaSuccess) {
     lv_set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
     return LV_E_NOMEM;

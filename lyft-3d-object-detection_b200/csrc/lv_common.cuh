@@ -103,6 +103,9 @@ struct lv_handle {
 
   // multi-sweep ingest
   lv_mirror ing_offsets, ing_tm, ing_lag, ing_has;
+
+  // PNG encoder: look-back descriptors and records per CTA; *_host staging (images, files, sizes)
+  lv_buffer png_state, png_rec, png_stage[3];
 };
 
 // every device buffer a handle owns (for lv_destroy / lv_workspace_bytes)
@@ -115,7 +118,8 @@ inline std::vector<lv_buffer*> lv_all_buffers(lv_handle* h) {
           &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_chunk_frame.dev, &h->vox_stage_points, &h->vox_stage_out[0],
           &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3], &h->flt_ranges, &h->flt_dst, &h->flt_tmp[0], &h->flt_tmp[1],
           &h->flt_tmp[2], &h->flt_tmp[3], &h->pil_map, &h->ing_offsets.dev,
-          &h->ing_tm.dev, &h->ing_lag.dev, &h->ing_has.dev};
+          &h->ing_tm.dev, &h->ing_lag.dev, &h->ing_has.dev, &h->png_state, &h->png_rec, &h->png_stage[0], &h->png_stage[1],
+          &h->png_stage[2]};
 }
 
 inline size_t lv_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

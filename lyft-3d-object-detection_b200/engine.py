@@ -82,10 +82,10 @@ class FrameBatchEngine:
                  voxel_size=synth.PILLAR_VOXEL_SIZE, pc_range=synth.PILLAR_RANGE,
                  max_points=synth.PILLAR_MAX_POINTS, max_voxels=synth.PILLAR_MAX_VOXELS,
                  canvas=synth.PILLAR_CANVAS, channels=synth.PILLAR_FEATURES, voxel_capacity=None,
-                 overflow="continue"):
+                 overflow="continue", handle=None):
         self.lib = nat.load()
         self.dev = torch.device("cuda", device)
-        self.h = nat.get_handle(device)
+        self.h = handle or nat.get_handle(device)
         apply_env_options(self.h)
         self.F = int(frames_per_step)
         self.n = int(points_per_frame)
@@ -119,10 +119,10 @@ class FrameBatchEngine:
         self.total_rows = None
 
     # ---- stages (all asynchronous on torch's current stream) -------------------------------
-    def bev(self, points):
+    def bev(self, points, handle=None):
         st = nat.current_stream_ptr(self.dev)
         nat.check(self.lib.lv_bev_rasterize(
-            self.h.ptr, points.data_ptr(), points.shape[1], self.F, self.offsets.ctypes.data, None, None, self.F,
+            (handle or self.h).ptr, points.data_ptr(), points.shape[1], self.F, self.offsets.ctypes.data, None, None, self.F,
             self._shape, self._vs, self.z_offset, self.max_intensity, None, self.bev_norm.data_ptr(),
             self.bev_u8.data_ptr(), None, None, st))
 
@@ -133,13 +133,17 @@ class FrameBatchEngine:
             self.voxels.data_ptr(), self.coords.data_ptr(), self.num_points.data_ptr(), self.voxel_num.data_ptr(),
             self.voxel_offsets.data_ptr(), st))
 
-    def pillarize(self, points):
-        """voxelize + decorate fused (lv_pillarize_concat): the (P,T,4) voxel tensor is never written."""
+    def pillarize(self, points, voxel_num=None, voxel_offsets=None):
+        """voxelize + decorate fused (lv_pillarize_concat): the (P,T,4) voxel tensor is never written.
+        voxel_num / voxel_offsets redirect the per-frame counts (a pipeline that copies them out while the
+        next step runs keeps one pair per slot)."""
         st = nat.current_stream_ptr(self.dev)
+        vn = self.voxel_num if voxel_num is None else voxel_num
+        vo = self.voxel_offsets if voxel_offsets is None else voxel_offsets
         nat.check(self.lib.lv_pillarize_concat(
             self.h.ptr, ctypes.byref(self.cfg), points.data_ptr(), self.F, self.offsets.ctypes.data, self.cap,
             self.vx, self.vy, self.x_off, self.y_off, 0, 0, self.decorated.data_ptr(), self.coords.data_ptr(),
-            self.num_points.data_ptr(), self.voxel_num.data_ptr(), self.voxel_offsets.data_ptr(), st))
+            self.num_points.data_ptr(), vn.data_ptr(), vo.data_ptr(), st))
 
     def pillar_features(self, points, weight, scale, shift):
         """voxelize + decorate + last PFNLayer (eval) fused (lv_pillarize_pfn_concat): points in,
@@ -173,6 +177,16 @@ class FrameBatchEngine:
         nat.check(self.lib.lv_pillar_scatter(
             self.h.ptr, feats.data_ptr(), self.coords.data_ptr(), rows, self.channels, self.F, self.ny, self.nx,
             self.canvas.data_ptr(), st))
+
+    def scatter_dev(self, voxel_offsets=None, features=None):
+        """Scatter with the pillar count read ON THE DEVICE (voxel_offsets[F], clamped to the capacity):
+        no host round trip between the voxelizer and the canvas."""
+        st = nat.current_stream_ptr(self.dev)
+        feats = self.features if features is None else features
+        vo = self.voxel_offsets if voxel_offsets is None else voxel_offsets
+        nat.check(self.lib.lv_pillar_scatter_dev(
+            self.h.ptr, feats.data_ptr(), self.coords.data_ptr(), vo[self.F:].data_ptr(), self.cap, self.channels,
+            self.F, self.ny, self.nx, self.canvas.data_ptr(), st))
 
     def step(self, points, pfn=None, fused=True):
         """One pass of both paths over a (F*n, 4) float32 CUDA tensor of points.  With LV_NVTX=1 the
@@ -221,11 +235,10 @@ class PipelinedEngine:
         s_sc  (low)   scatter(i) waits for s_vox(i)   <- buffer set i % 2, pillar count read on the
                                                          device (lv_pillar_scatter_dev)
 
-    so scatter(i) may overlap BEV(i+1) and the voxelizer of step i+1.  Measured (profiles/README.md):
-    1.855 ms per step with the host read, 1.816 ms without it on one stream, 1.755 ms on three
-    streams - most of the gain is the missing host round trip, kernels of different streams
-    overlap little because the canvas kernel fills every SM.  Results are identical to
-    FrameBatchEngine.step (tests/test_gpu_engine.py); set 0 aliases the engine's own buffers.
+    so scatter(i) may overlap BEV(i+1) and the voxelizer of step i+1.  Every stream drives ITS OWN
+    library handle (include/lyft_voxel.h: one handle per (process, device, stream)), so no workspace
+    is shared between streams.  Results are identical to FrameBatchEngine.step
+    (tests/test_gpu_engine.py); set 0 aliases the engine's own buffers.
     """
 
     def __init__(self, engine, bev_priority=-1, vox_priority=-1, scatter_priority=0):
@@ -234,6 +247,9 @@ class PipelinedEngine:
         self.s_bev = torch.cuda.Stream(d, priority=bev_priority)
         self.s_vox = torch.cuda.Stream(d, priority=vox_priority)
         self.s_sc = torch.cuda.Stream(d, priority=scatter_priority)
+        self.h_bev, self.h_vox, self.h_sc = (nat.Handle(d.index) for _ in range(3))
+        for h in (self.h_bev, self.h_vox, self.h_sc):
+            apply_env_options(h)
         self.sets = [dict(coords=e.coords, num_points=e.num_points, voxel_num=e.voxel_num,
                           voxel_offsets=e.voxel_offsets, decorated=e.decorated)]
         self.sets.append(dict(coords=torch.empty_like(e.coords), num_points=torch.empty_like(e.num_points),
@@ -243,6 +259,9 @@ class PipelinedEngine:
         self.ev_sc = [torch.cuda.Event() for _ in range(2)]    # scatter has consumed the set
         self.ev_bev = torch.cuda.Event()
         self.i = 0
+
+    def launches(self):
+        return self.h_bev.launches() + self.h_vox.launches() + self.h_sc.launches()
 
     def submit(self, points, features=None):
         """Enqueues one step over `points` (valid on the caller's current stream) and returns
@@ -255,14 +274,14 @@ class PipelinedEngine:
         ready.record(cur)
         with torch.cuda.stream(self.s_bev):
             self.s_bev.wait_event(ready)
-            e.bev(points)
+            e.bev(points, handle=self.h_bev)
             self.ev_bev.record(self.s_bev)
         with torch.cuda.stream(self.s_vox):
             self.s_vox.wait_event(ready)
             if self.i >= 2:
                 self.s_vox.wait_event(self.ev_sc[k])     # scatter(i-2) has read this set
             nat.check(e.lib.lv_pillarize_concat(
-                e.h.ptr, ctypes.byref(e.cfg), points.data_ptr(), e.F, e.offsets.ctypes.data, e.cap, e.vx, e.vy,
+                self.h_vox.ptr, ctypes.byref(e.cfg), points.data_ptr(), e.F, e.offsets.ctypes.data, e.cap, e.vx, e.vy,
                 e.x_off, e.y_off, 0, 0, st["decorated"].data_ptr(), st["coords"].data_ptr(),
                 st["num_points"].data_ptr(), st["voxel_num"].data_ptr(), st["voxel_offsets"].data_ptr(),
                 self.s_vox.cuda_stream))
@@ -271,7 +290,7 @@ class PipelinedEngine:
             self.s_sc.wait_event(self.ev_vox[k])
             feats = e.features if features is None else features
             nat.check(e.lib.lv_pillar_scatter_dev(
-                e.h.ptr, feats.data_ptr(), st["coords"].data_ptr(), st["voxel_offsets"][e.F:].data_ptr(), e.cap,
+                self.h_sc.ptr, feats.data_ptr(), st["coords"].data_ptr(), st["voxel_offsets"][e.F:].data_ptr(), e.cap,
                 e.channels, e.F, e.ny, e.nx, e.canvas.data_ptr(), self.s_sc.cuda_stream))
             self.ev_sc[k].record(self.s_sc)
         self.i += 1
@@ -286,32 +305,81 @@ class PipelinedEngine:
             cur.wait_event(ev)
 
 
-class HostPipeline:
-    """End-to-end driver with HOST buffers on both sides of a FrameBatchEngine.
+class MappedBuffer:
+    """Mapped pinned host memory (lv_host_alloc) seen as a torch CPU tensor.  Under unified addressing the
+    tensor's data_ptr() is also valid inside kernels, so a kernel can write its result straight into host
+    memory (lv_png_encode) and a cudaMemcpyAsync into it is a true asynchronous pinned copy."""
 
-    Pinned host points are copied in on a copy stream, both paths run on the compute
-    stream, and the BEV u8 images + per-frame pillar counts are copied back to pinned host
-    memory on a third stream; the H2D of step i+1 and the D2H of step i-1 overlap the
-    kernels of step i (two device input slots).  The canvas stays on the device - its
-    consumer is the RPN (second/second/pytorch/models/voxelnet.py:336).
+    def __init__(self, shape, dtype):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        p = ctypes.c_void_p()
+        nat.check(nat.load().lv_host_alloc(max(n, 1), ctypes.byref(p)))
+        self.ptr = p
+        self._raw = (ctypes.c_uint8 * max(n, 1)).from_address(p.value)
+        self.tensor = torch.frombuffer(self._raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self.ptr is not None:
+            self.tensor = None
+            self._raw = None
+            nat.load().lv_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostPipeline:
+    """End-to-end driver with HOST buffers on both sides of a FrameBatchEngine, no host synchronisation
+    inside the loop.
+
+        s_in      pinned host points -> device slot (i+1) & 1            (overlaps the kernels of step i)
+        compute   pillarize -> scatter (pillar count read on the device)
+                  BEV -> u8 images -> lv_png_encode: the "{token}_input.png" FILES of
+                  generating_train_bev.py:215 are written by the kernels straight into mapped pinned host
+                  memory (slot i & 1), ~20 KB per frame instead of the 338 KB dense image (98 % zeros);
+                  per-frame file sizes and pillar counts follow the same way.
+
+    The canvas stays on the device - its consumer is the RPN (second/second/pytorch/models/voxelnet.py:336).
+    Every per-step output that leaves the device exists once per slot (png, sizes, voxel_num,
+    voxel_offsets), so step i+1 never overwrites what step i still hands to the host.
+    `consume(step, slot_view)` - if given - runs on the host for step i-1 after step i was enqueued (it
+    waits for that step's event only): the place where a dataset generator writes the files.
     """
 
-    def __init__(self, engine, fused=True):
-        self.eng = engine
+    def __init__(self, engine, fused=True, png=True, png_stride=None):
+        self.eng = e = engine
         self.fused = fused
-        dev = engine.dev
-        n_rows = engine.F * engine.n
+        self.png = png
+        dev = e.dev
+        n_rows = e.F * e.n
         self.s_in = torch.cuda.Stream(dev)
-        self.s_out = torch.cuda.Stream(dev)
         self.dev_pts = [torch.empty((n_rows, 4), dtype=torch.float32, device=dev) for _ in range(2)]
         self.ev_in = [torch.cuda.Event() for _ in range(2)]      # H2D of slot done
         self.ev_free = [torch.cuda.Event() for _ in range(2)]    # kernels reading slot done
-        self.ev_bev = torch.cuda.Event()                         # BEV outputs of the step ready
-        self.ev_out = torch.cuda.Event()                         # D2H of the step done
-        self.host_u8 = torch.empty(engine.bev_u8.shape, dtype=torch.uint8, pin_memory=True)
-        self.host_vnum = torch.empty((engine.F,), dtype=torch.int32, pin_memory=True)
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]    # every host-visible result of the slot is written
+        S0, S1, S2 = e.bev_shape
+        from . import bev as _bev
+        self.png_stride = int(png_stride or min(_bev.png_slot_bytes(S0, S1, S2), 96 * 1024))
+        self.vnum = [torch.empty_like(e.voxel_num) for _ in range(2)]
+        self.voff = [torch.empty_like(e.voxel_offsets) for _ in range(2)]
+        self._mapped = []
+
+        def mapped(shape, dtype):
+            m = MappedBuffer(shape, dtype)
+            self._mapped.append(m)
+            return m.tensor
+        if png:
+            self.host_png = [mapped((e.F, self.png_stride), torch.uint8) for _ in range(2)]
+            self.host_sizes = [mapped((e.F,), torch.int32) for _ in range(2)]
+        else:
+            self.host_u8 = [mapped(tuple(e.bev_u8.shape), torch.uint8) for _ in range(2)]
+        self.host_vnum = [mapped((e.F,), torch.int32) for _ in range(2)]
         self.h2d_bytes = n_rows * 16
-        self.d2h_bytes = self.host_u8.numel() + self.host_vnum.numel() * 4
+        self.d2h_bytes = None          # measured by run(): bytes that crossed to the host per step
 
     def _issue_h2d(self, slot, host_pts):
         with torch.cuda.stream(self.s_in):
@@ -319,40 +387,63 @@ class HostPipeline:
             self.dev_pts[slot].copy_(host_pts, non_blocking=True)
             self.ev_in[slot].record(self.s_in)
 
-    def run(self, host_batches, steps):
-        """Processes `steps` batches (host_batches[i % len]) and returns when every
-        result of the last step is in host memory."""
+    def slot_view(self, slot):
+        """Host-side results of a finished slot: {"png": [bytes...]} or {"u8": array}, "voxel_num"."""
+        out = {"voxel_num": self.host_vnum[slot].numpy()}
+        if self.png:
+            sizes = self.host_sizes[slot].numpy()
+            out["sizes"] = sizes
+            out["png"] = self.host_png[slot].numpy()
+        else:
+            out["u8"] = self.host_u8[slot].numpy()
+        return out
+
+    def run(self, host_batches, steps, consume=None):
+        """Processes `steps` batches (host_batches[i % len]) and returns when every result of the last
+        step is in host memory.  Returns the number of bytes the last step sent to the host."""
         eng = self.eng
         cur = torch.cuda.current_stream(eng.dev)
         for ev in self.ev_free:
             ev.record(cur)
-        self.ev_out.record(cur)
         self._issue_h2d(0, host_batches[0])
-        rows = 0
         for i in range(steps):
             slot = i & 1
             if i + 1 < steps:
                 self._issue_h2d(slot ^ 1, host_batches[(i + 1) % len(host_batches)])
             cur.wait_event(self.ev_in[slot])
             pts = self.dev_pts[slot]
-            # pillar path first: it does not touch the BEV buffers still being copied out
             if self.fused:
-                eng.pillarize(pts)
-                rows = eng.read_total_rows()
+                eng.pillarize(pts, self.vnum[slot], self.voff[slot])
             else:
-                eng.voxelize(pts)
-                rows = eng.read_total_rows()
-                eng.decorate(rows)
-            eng.scatter(rows)
-            cur.wait_event(self.ev_out)          # previous step's images have left the device
+                raise nat.LyftVoxelError(nat.LV_E_UNSUPPORTED, "HostPipeline runs the fused pillar path only")
+            eng.scatter_dev(self.voff[slot])
             eng.bev(pts)
             self.ev_free[slot].record(cur)
-            self.ev_bev.record(cur)
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(self.ev_bev)
-                self.host_u8.copy_(eng.bev_u8, non_blocking=True)
-                self.host_vnum.copy_(eng.voxel_num, non_blocking=True)
-                self.ev_out.record(self.s_out)
-        self.ev_out.synchronize()
+            if self.png:
+                nat.check(eng.lib.lv_png_encode(
+                    eng.h.ptr, eng.bev_u8.data_ptr(), eng.F, eng.bev_shape[0], eng.bev_shape[1], eng.bev_shape[2], 1,
+                    self.host_png[slot].data_ptr(), self.png_stride, self.host_sizes[slot].data_ptr(), cur.cuda_stream))
+            else:
+                self.host_u8[slot].copy_(eng.bev_u8, non_blocking=True)
+            self.host_vnum[slot].copy_(self.vnum[slot], non_blocking=True)
+            self.ev_done[slot].record(cur)
+            if consume is not None and i > 0:
+                self.ev_done[slot ^ 1].synchronize()
+                consume(i - 1, self.slot_view(slot ^ 1))
+        last = (steps - 1) & 1
+        self.ev_done[last].synchronize()
+        if consume is not None and steps > 0:
+            consume(steps - 1, self.slot_view(last))
         cur.synchronize()
-        return rows
+        if self.png:
+            sizes = self.host_sizes[last].numpy()
+            if (sizes <= 0).any():
+                raise nat.LyftVoxelError(nat.LV_E_INVALID, "a PNG slot of %d bytes is too small (needs %d)" %
+                                         (self.png_stride, int(-sizes.min())))
+            self.d2h_bytes = int(sizes.sum()) + 8 * eng.F
+        else:
+            self.d2h_bytes = int(self.host_u8[last].numel()) + 4 * eng.F
+        total = int(self.host_vnum[last].numpy().sum())
+        if total > eng.cap:
+            raise nat.LyftVoxelError(nat.LV_E_INVALID, "voxel capacity %d exceeded (%d rows)" % (eng.cap, total))
+        return self.d2h_bytes

@@ -232,3 +232,88 @@ def test_full_size_batch_properties():
         total_kept += int(nump.sum())
     nz = (eng.canvas.abs().sum(dim=1) > 0).sum()
     assert int(nz) == rows
+
+
+def test_host_pipeline_every_step_matches_the_serial_engine():
+    """HostPipeline (pinned host points in; PNG files, file sizes and pillar counts written into mapped host
+    memory; no host sync inside the loop): the host-side results of EVERY step equal FrameBatchEngine.step on
+    the same batch - the per-slot voxel_num / offsets keep step i+1 from overwriting what step i hands out."""
+    import torch
+    from lyft3d_b200.engine import FrameBatchEngine, HostPipeline
+    from oracle import png_oracle
+    F = 4
+    host_batches, want = [], []
+    for b in range(3):
+        # batches of different density, so that consecutive steps have different pillar counts
+        frames = [synth.c5_frame(500 + 10 * b + f)[:(b + 1) * 15000] for f in range(F)]
+        frames = [np.concatenate([fr, np.full((45000 - fr.shape[0], 4), 1e6, np.float32)]) for fr in frames]
+        hb = torch.from_numpy(np.concatenate(frames)).pin_memory()
+        host_batches.append(hb)
+    n = host_batches[0].shape[0] // F
+    eng = FrameBatchEngine(0, F, n)
+    torch.manual_seed(11)
+    eng.features.copy_(torch.randn_like(eng.features))
+    for hb in host_batches:
+        rows = eng.step(hb.cuda())
+        want.append((eng.voxel_num.cpu().numpy().copy(), eng.bev_u8.cpu().numpy().copy(), eng.canvas.clone()))
+    assert len({tuple(w[0]) for w in want}) == 3
+    pipe = HostPipeline(eng)
+    seen = {}
+
+    def consume(step, view):
+        sizes = view["sizes"].copy()
+        seen[step] = (view["voxel_num"].copy(), [view["png"][f, :sizes[f]].tobytes() for f in range(F)])
+
+    steps = 7
+    pipe.run(host_batches, steps, consume=consume)
+    assert sorted(seen) == list(range(steps))
+    for i in range(steps):
+        vnum, u8, _ = want[i % 3]
+        assert np.array_equal(seen[i][0], vnum), "step %d: pillar counts of another step" % i
+        for f in range(F):
+            assert seen[i][1][f] == png_oracle.encode_png(u8[f]), "step %d frame %d" % (i, f)
+    assert bool((eng.canvas == want[(steps - 1) % 3][2]).all())
+    assert pipe.d2h_bytes * 10 < eng.bev_u8.numel()
+    # the dense-image variant (no PNG) hands out the u8 images themselves
+    pipe2 = HostPipeline(eng, png=False)
+    got = {}
+    pipe2.run(host_batches, 4, consume=lambda i, v: got.__setitem__(i, (v["voxel_num"].copy(), v["u8"].copy())))
+    for i in range(4):
+        assert np.array_equal(got[i][0], want[i % 3][0]) and np.array_equal(got[i][1], want[i % 3][1])
+
+
+@pytest.mark.parametrize("T", [17, 20, 31, 32, 33])
+def test_fused_pillarize_small_max_points(T):
+    """max_points between 17 and 33 with DENSE pillars (the two-pillars-per-warp path shares
+    the warp's stage and needs T >= 32): fused voxelize+decorate == voxelize then decorate, bit for bit, and
+    the fused PFN == the unfused PFN kernel."""
+    import torch
+    from lyft3d_b200 import pointpillars as pp
+    from lyft3d_b200.engine import FrameBatchEngine
+    F, n = 3, 30000
+    rng = np.random.default_rng(T)
+    frames = []
+    for f in range(F):
+        # clusters of 1..24 points per pillar around a few hundred pillar centres
+        centres = rng.uniform(-40, 40, (600, 2))
+        k = rng.integers(0, 600, n)
+        xy = centres[k] + rng.uniform(-0.12, 0.12, (n, 2))
+        frames.append(np.concatenate([xy, rng.uniform(-2, 2, (n, 1)), rng.random((n, 1))], axis=1).astype(np.float32))
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    eng = FrameBatchEngine(0, F, n, max_points=T)
+    eng.voxelize(pts)
+    rows = eng.read_total_rows()
+    assert int(eng.num_points[:rows].max()) == T and int((eng.num_points[:rows] <= 16).sum()) > 0
+    eng.decorate(rows)
+    unfused = eng.decorated[:rows].clone()
+    eng.decorated.fill_(float("nan"))
+    eng.pillarize(pts)
+    assert eng.read_total_rows() == rows
+    assert bool((eng.decorated[:rows] == unfused).all())
+    net = pp.PillarFeatureNet(4, True, (64,), False, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE).cuda().eval()
+    w, sc, sh = pp.fold_pfn_layer(net.pfn_layers[0])
+    eng.pillar_features(pts, w, sc, sh)
+    fused = eng.features[:rows].clone()
+    ref = pp.pillar_pfn(eng.voxels[:rows], eng.num_points[:rows], eng.coords[:rows], net.vx, net.vy, net.x_offset,
+                        net.y_offset, w, sc, sh)
+    assert bool((fused == ref).all())
