@@ -169,6 +169,14 @@ int lv_set_option(lv_handle* h, const char* name, int64_t value) {
     h->vox_frame_kernel = value;
     return LV_OK;
   }
+  if (strcmp(name, "vox_list_path") == 0) {
+    h->vox_list_path = value;
+    return LV_OK;
+  }
+  if (strcmp(name, "vox_rows_waves") == 0) {
+    h->vox_rows_waves = value;
+    return LV_OK;
+  }
   if (strcmp(name, "canvas_variant") == 0) {
     h->canvas_variant = value;
     return LV_OK;

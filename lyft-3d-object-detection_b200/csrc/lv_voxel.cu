@@ -902,7 +902,7 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : VX_BINS_M
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
     for (int j = threadIdx.x; j < total4; j += VX_THREADS) {
-      const int v = (int)(((unsigned long long)(unsigned)j * p.row_div_m) >> 32);   // j / T (j < 2^20)
+      const int v = p.T == 1 ? j : (int)(((unsigned long long)(unsigned)j * p.row_div_m) >> 32);   // j / T (j < 2^20; ceil(2^32 / 1) does not fit)
       const int r = j - v * p.T;
       float4 o = z4;
       if (r < total[v]) o = __ldg(pts4 + slot_tab[v * p.T + r]);
@@ -1031,6 +1031,8 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : VX_BINS_M
     }
   }
 }
+
+#include "lv_voxel_list.cuh"
 
 // rows [voxel_num, V) of the padded layout (generate_multi_gpu, preprocess.py:311-317)
 __global__ void __launch_bounds__(VX_THREADS) vx_zero_tail_kernel(VoxParams p) {
@@ -1283,6 +1285,26 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     }
   }
 
+  // list path (lv_voxel_list.cuh): three kernels, order rebuilt inside the warp that writes the row.  Small dense
+  // maps only (8 bytes per cell), 4-float points, rows of at most 64 slots.  OPT-IN (lv_set_option "vox_list_path" 1):
+  // bit-identical, but measured slower on 128 C5 frames (see the header of lv_voxel_list.cuh).
+  const bool list_path = h->vox_list_path == 1 && frame_cs == 0 && !mean_channels && c4 && T <= 64 && (deco || out4) &&
+                         G * 8 <= (64ll << 20) && max_frame_pts < (1ll << VL_RANK_BITS);
+  size_t smem_rows = 0;
+  if (list_path) {
+    const int64_t budget2 = h->vox_dense_map_limit_bytes > 0 ? h->vox_dense_map_limit_bytes : (192ll << 20);
+    fif = budget2 / (G * 8);
+    if (fif < 1) fif = 1;
+    if (fif > 2048) fif = 2048;
+    if (fif > n_frames) fif = n_frames;
+    fif = lv_div_up(n_frames, lv_div_up(n_frames, fif));
+    smem_rows = ((size_t)((2 * (fif + 1) + 3) & ~3) + VX_WARPS * 64) * 4 + deco_stage;
+    if (pfn) LV_CHECK(vx_set_smem(vl_rows_kernel<VX_OUT_PFN>, smem_rows));
+    else if (deco) LV_CHECK(vx_set_smem(vl_rows_kernel<VX_OUT_DECORATE>, smem_rows));
+    else LV_CHECK(vx_set_smem(vl_rows_kernel<VX_OUT_VOXELS>, smem_rows));
+    LV_CHECK(vx_set_smem(vl_cells_kernel<true>, p.tma_bytes));
+  }
+
   int f0 = 0;
   while (f0 < n_frames) {
     int f1 = f0 + 1;
@@ -1292,6 +1314,53 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     const int chunk_lo = frame_chunk[f0], nchunks = frame_chunk[f1] - chunk_lo;
     p.f0 = f0; p.f1 = f1; p.chunk_lo = chunk_lo; p.pt_lo = pt_lo;
 
+    if (list_path) {
+      LV_CHECK(h->vox_map.ensure((size_t)nf * G * 8, stream, 0x7f));
+      LV_CHECK(h->vox_cell.ensure((size_t)(npts + 1) * 4 * 2, stream));            // cell + arrival rank
+      LV_CHECK(h->vox_vals[0].ensure((size_t)(npts + 1) * 4, stream));             // lists
+      LV_CHECK(h->vox_vrec.ensure((size_t)(npts + 1) * 16, stream));               // per-voxel records
+      LV_CHECK(h->vox_chunk.ensure((size_t)(nchunks + 1) * 8, stream));            // look-back descriptors
+      LV_CHECK(h->vox_frame_state.ensure((size_t)nf * 2 * 4, stream));
+      p.map = h->vox_map.as<int32_t>();
+      p.cell = h->vox_cell.as<int32_t>();
+      p.chunk_state = h->vox_chunk.as<unsigned long long>();
+      VlParams q;
+      q.map2 = h->vox_map.as<unsigned long long>();
+      q.arr = h->vox_cell.as<uint32_t>() + (npts + 1);
+      q.list = h->vox_vals[0].as<int32_t>();
+      q.vrec = h->vox_vrec.as<int4>();
+      q.frame_total = h->vox_frame_state.as<int32_t>();
+      if (nchunks > 0) {
+        vl_cells_kernel<true><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p, q);
+        LV_LAUNCH_CHECK(h);
+        vl_assign_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p, q);
+        LV_LAUNCH_CHECK(h);
+      }
+      // frames without points never ran L2: their totals are set here
+      bool any_empty = false;
+      for (int f = f0; f < f1; ++f) any_empty |= frame_chunk[f + 1] == frame_chunk[f];
+      if (any_empty || nchunks == 0) {
+        vl_empty_frames_kernel<<<(unsigned)lv_div_up(nf, 256), 256, 0, stream>>>(p, q);
+        LV_LAUNCH_CHECK(h);
+      }
+      const int minb = pfn ? 3 : VX_BINS_MINB;
+      int64_t grid_r = (int64_t)h->num_sms * minb * (h->vox_rows_waves > 0 ? h->vox_rows_waves : 4);
+      const int64_t max_blocks = lv_div_up(npts < (int64_t)nf * G ? npts : (int64_t)nf * G, VL_ITEMS_PER_CTA);
+      if (grid_r > max_blocks) grid_r = max_blocks;
+      if (grid_r < 1) grid_r = 1;
+      if (pfn) vl_rows_kernel<VX_OUT_PFN><<<(unsigned)grid_r, VX_THREADS, smem_rows, stream>>>(p, q, dcfg, d_decorated, pcfg);
+      else if (deco) vl_rows_kernel<VX_OUT_DECORATE><<<(unsigned)grid_r, VX_THREADS, smem_rows, stream>>>(p, q, dcfg, d_decorated, pcfg);
+      else vl_rows_kernel<VX_OUT_VOXELS><<<(unsigned)grid_r, VX_THREADS, smem_rows, stream>>>(p, q, dcfg, nullptr, pcfg);
+      LV_LAUNCH_CHECK(h);
+      if (!concat && cfg->zero_tail) {
+        int gx = (int)lv_div_up((int64_t)h->num_sms * 8, nf);
+        if (gx > V) gx = V;
+        vx_zero_tail_kernel<<<dim3((unsigned)gx, (unsigned)nf), VX_THREADS, 0, stream>>>(p);
+        LV_LAUNCH_CHECK(h);
+      }
+      f0 = f1;
+      continue;
+    }
     if (frame_cs == 0) LV_CHECK(h->vox_map.ensure((size_t)nf * G * 4, stream, 0x7f));
     LV_CHECK(h->vox_cell.ensure((size_t)(npts + 1) * 4 * 2, stream));            // cell + key0
     LV_CHECK(h->vox_keys[0].ensure((size_t)(npts + 1) * 4, stream));

@@ -35,7 +35,8 @@ def shard_frames(n_frames, rank, world_size):
 ENV_OPTIONS = {"LV_VOX_MAP_MB": ("vox_dense_map_limit_bytes", 1 << 20), "LV_BEV_TMA": ("bev_tma", 1),
                "LV_DISABLE_TMA": ("disable_tma", 1), "LV_BEV_FIF": ("bev_frames_in_flight", 1),
                "LV_CANVAS_VARIANT": ("canvas_variant", 1),
-               "LV_VOX_FRAME_KERNEL": ("vox_frame_kernel", 1)}
+               "LV_VOX_FRAME_KERNEL": ("vox_frame_kernel", 1), "LV_VOX_LIST_PATH": ("vox_list_path", 1),
+               "LV_VOX_ROWS_WAVES": ("vox_rows_waves", 1)}
 
 
 def apply_env_options(handle):
