@@ -408,6 +408,21 @@ int lv_pillar_scatter_dev(lv_handle* h, const float* d_feats, const int32_t* d_c
                           int32_t batch_size, int32_t ny, int32_t nx, float* d_canvas,
                           lv_stream stream);
 
+/* Half-precision forms (apex O2: second/second/pytorch/train.py:34-47 casts "voxels" to half,
+ * second/configs/nuscenes/all.pp.mida.config:348; the canvas follows voxel_features.dtype,
+ * pointpillars.py:449-452).  float16 arrays are passed as uint16_t*.
+ * lv_pillar_decorate_half reproduces torch's half arithmetic - every op computes in float32 and rounds
+ * its result to half - statement by statement (pointpillars.py:203-231 and the variants): needs
+ * num_features == 4 and max_points <= 64.  lv_pillar_scatter_half writes the (B,C,ny,nx) float16 canvas
+ * in one pass, every element exactly once, bit-exact. */
+int lv_pillar_decorate_half(lv_handle* h, const uint16_t* d_voxels, const int32_t* d_num_points,
+                            const int32_t* d_coors, int64_t n_pillars, int32_t max_points, int32_t num_features,
+                            float vx, float vy, float x_offset, float y_offset, int32_t variant,
+                            int32_t with_distance, uint16_t* d_out, lv_stream stream);
+int lv_pillar_scatter_half(lv_handle* h, const uint16_t* d_feats, const int32_t* d_coords, int64_t n_pillars,
+                           int32_t channels, int32_t batch_size, int32_t ny, int32_t nx, uint16_t* d_canvas,
+                           lv_stream stream);
+
 /* SimpleVoxel.forward (second/second/pytorch/models/voxel_encoder.py:219-225):
  * out[p, c] = sum_t voxels[p, t, c] / num[p] for c < num_features_out. */
 int lv_voxel_mean(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,

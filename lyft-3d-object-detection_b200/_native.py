@@ -113,6 +113,9 @@ SIGNATURES = {
                                                _vp, _vp]),
     "lv_pillar_scatter": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lv_pillar_scatter_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "lv_pillar_decorate_half": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _i32, _i32,
+                                               _vp, _vp]),
+    "lv_pillar_scatter_half": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lv_voxel_mean": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
 }
 

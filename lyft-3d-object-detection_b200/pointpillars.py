@@ -17,7 +17,9 @@ checkpoints load and ``module_class_name`` in a config resolves unchanged.
       ``voxel_features`` (the backward is a torch gather of the canvas gradient).
   SimpleVoxel / SimpleVoxelRadius  (voxel_encoder.py:207-255) via lv_voxel_mean.
 
-CUDA float32 tensors only; anything else raises - there is no CPU path.
+CUDA float32 tensors, and float16 ones for the decoration and the scatter (apex O2,
+second/second/pytorch/train.py:34-47: "voxels" arrive as half); anything else raises - there is no
+CPU path.
 """
 import numpy as np
 import torch
@@ -69,11 +71,12 @@ def get_paddings_indicator(actual_num, max_num, axis=0):
     return actual_num.int() > steps
 
 
-def _require_cuda_f32(t, name):
+def _require_cuda_f32(t, name, half_ok=False):
     if not (isinstance(t, torch.Tensor) and t.is_cuda):
         raise nat.LyftVoxelError(nat.LV_E_NODEVICE, "%s must be a CUDA tensor (no CPU fallback)" % name)
-    if t.dtype != torch.float32:
-        raise nat.LyftVoxelError(nat.LV_E_INVALID, "%s must be float32, got %s" % (name, t.dtype))
+    if t.dtype != torch.float32 and not (half_ok and t.dtype == torch.float16):
+        raise nat.LyftVoxelError(nat.LV_E_INVALID, "%s must be float32%s, got %s" %
+                                 (name, " or float16" if half_ok else "", t.dtype))
 
 
 def _f32(x):
@@ -84,8 +87,9 @@ def _f32(x):
 def decorate_pillars(features, num_voxels, coors, vx, vy, x_offset, y_offset, variant="pfn",
                      with_distance=False):
     """Fused decoration: (P,T,C) float32 -> (P,T,C_out) float32, padding rows zero.
-    pointpillars.py:203-231 (+ :117-145, :290-319, :378-411)."""
-    _require_cuda_f32(features, "features")
+    pointpillars.py:203-231 (+ :117-145, :290-319, :378-411).  float16 features (apex O2) give a float16
+    result with torch's half roundings (lv_pillar_decorate_half)."""
+    _require_cuda_f32(features, "features", half_ok=True)
     lib = nat.load()
     features = features.contiguous()
     P, T, C = features.shape
@@ -95,8 +99,15 @@ def decorate_pillars(features, num_voxels, coors, vx, vy, x_offset, y_offset, va
     c_out = lib.lv_pillar_out_channels(C, v, int(bool(with_distance)))
     if c_out <= 0:
         raise nat.LyftVoxelError(nat.LV_E_INVALID, "bad num_features %d" % C)
-    out = torch.empty((P, T, c_out), dtype=torch.float32, device=features.device)
+    out = torch.empty((P, T, c_out), dtype=features.dtype, device=features.device)
     h = nat.get_handle(features.device.index)
+    if features.dtype == torch.float16:
+        with torch.cuda.device(features.device):
+            nat.check(lib.lv_pillar_decorate_half(h.ptr, features.data_ptr(), num.data_ptr(), co.data_ptr(), P, T, C,
+                                                  _f32(vx), _f32(vy), _f32(x_offset), _f32(y_offset), v,
+                                                  int(bool(with_distance)), out.data_ptr(),
+                                                  nat.current_stream_ptr(features.device)))
+        return out
     with torch.cuda.device(features.device):
         nat.check(lib.lv_pillar_decorate(h.ptr, features.data_ptr(), num.data_ptr(), co.data_ptr(), P, T, C,
                                          _f32(vx), _f32(vy), _f32(x_offset), _f32(y_offset), v,
@@ -203,7 +214,7 @@ class _PillarFeatureNetBase(nn.Module):
     def can_fuse(self, features):
         """The fused kernel is inference-only: eval mode, one PFNLayer, 4 input features,
         <= 64 points per pillar, 32/64/128 units, and nothing that needs a gradient."""
-        if self.training or len(self.pfn_layers) != 1:
+        if self.training or len(self.pfn_layers) != 1 or features.dtype != torch.float32:
             return False
         layer = self.pfn_layers[0]
         if features.dim() != 3 or features.shape[2] != 4 or features.shape[1] > 64 or layer.units not in (32, 64, 128):
@@ -262,11 +273,12 @@ class _ScatterFn(torch.autograd.Function):
         feats = voxel_features.contiguous()
         co = coords.to(torch.int32).contiguous()
         P, C = feats.shape
-        canvas = torch.empty((batch_size, C, ny, nx), dtype=torch.float32, device=feats.device)
+        canvas = torch.empty((batch_size, C, ny, nx), dtype=feats.dtype, device=feats.device)
         h = nat.get_handle(feats.device.index)
+        fn = lib.lv_pillar_scatter_half if feats.dtype == torch.float16 else lib.lv_pillar_scatter
         with torch.cuda.device(feats.device):
-            nat.check(lib.lv_pillar_scatter(h.ptr, feats.data_ptr(), co.data_ptr(), P, C, batch_size, ny, nx,
-                                            canvas.data_ptr(), nat.current_stream_ptr(feats.device)))
+            nat.check(fn(h.ptr, feats.data_ptr(), co.data_ptr(), P, C, batch_size, ny, nx,
+                         canvas.data_ptr(), nat.current_stream_ptr(feats.device)))
         ctx.save_for_backward(co)
         ctx.dims = (ny, nx)
         return canvas
@@ -280,8 +292,9 @@ class _ScatterFn(torch.autograd.Function):
 
 
 def scatter_pillars(voxel_features, coords, batch_size, ny, nx):
-    """canvas[b,:,y,x] = voxel_features[p] for coords[p] = (b,.,y,x); zeros elsewhere."""
-    _require_cuda_f32(voxel_features, "voxel_features")
+    """canvas[b,:,y,x] = voxel_features[p] for coords[p] = (b,.,y,x); zeros elsewhere.  The canvas has the
+    dtype of voxel_features (pointpillars.py:449-452): float32, or float16 under apex O2 - written in one pass."""
+    _require_cuda_f32(voxel_features, "voxel_features", half_ok=True)
     return _ScatterFn.apply(voxel_features, coords, int(batch_size), int(ny), int(nx))
 
 
@@ -299,10 +312,6 @@ class PointPillarsScatter(nn.Module):
         self.nchannels = num_input_features
 
     def forward(self, voxel_features, coords, batch_size):
-        if voxel_features.dtype != torch.float32:
-            # fp16 under apex O2 (train.py:223-228): compute in fp32, return the input dtype
-            return scatter_pillars(voxel_features.float(), coords, batch_size, self.ny, self.nx).to(
-                voxel_features.dtype)
         return scatter_pillars(voxel_features, coords, batch_size, self.ny, self.nx)
 
 

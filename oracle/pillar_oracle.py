@@ -107,3 +107,51 @@ def merge_batch_coords(coords_list):
     for i, c in enumerate(coords_list):
         out.append(np.pad(c, ((0, 0), (1, 0)), mode="constant", constant_values=i))
     return np.concatenate(out, axis=0)
+
+
+def decorate_half(voxels_h, num_points, coors, voxel_size, pc_range, variant="pfn", with_distance=False):
+    """The same decoration on float16 pillars (apex O2: second/second/pytorch/train.py:34-47 casts "voxels" to
+    half, configs/nuscenes/all.pp.mida.config:348): every torch op on half tensors computes in float32 and rounds
+    its RESULT to half, so each statement of pointpillars.py:203-231 contributes one rounding:
+        mean   = rh(rh(sum_T x) / num)              (:208-209, the sum accumulates in float32)
+        f_clus = rh(x - mean)                       (:210)
+        centre = rh(rh(coor * vx) + x_offset)       (:213-217; coors.to(half) is exact below 2048)
+        f_cent = rh(x - centre)
+        radius = rh(sqrt(x^2 + y^2)), dist = rh(sqrt(x^2 + y^2 + z^2))   (torch.norm accumulates in float32)
+    Returns float16 (P,T,C')."""
+    f32, f16 = np.float32, np.float16
+
+    def rh(a):
+        return np.asarray(a, dtype=f32).astype(f16).astype(f32)
+
+    v = np.asarray(voxels_h, dtype=f16).astype(f32)
+    P, T, C = v.shape
+    num = np.asarray(num_points)
+    vx, vy = float(voxel_size[0]), float(voxel_size[1])
+    x_off = vx / 2 + float(pc_range[0])
+    y_off = vy / 2 + float(pc_range[1])
+    mean = rh(rh(v[:, :, :3].sum(axis=1, keepdims=True, dtype=f32)) / rh(num.astype(f32)).reshape(-1, 1, 1))
+    f_cluster = rh(v[:, :, :3] - mean)
+    cx = rh(rh(coors[:, 3].astype(f32)[:, None] * f32(vx)) + f32(x_off))
+    cy = rh(rh(coors[:, 2].astype(f32)[:, None] * f32(vy)) + f32(y_off))
+    f_center = rh(np.stack([v[:, :, 0] - cx, v[:, :, 1] - cy], axis=-1))
+    if variant == "pfn":
+        head = v
+    elif variant == "old":
+        head = v.copy()
+        head[:, :, :2] = f_center
+    elif variant in ("radius", "radius_height"):
+        r = rh(np.sqrt(v[:, :, 0] * v[:, :, 0] + v[:, :, 1] * v[:, :, 1], dtype=f32))[..., None]
+        head = np.concatenate([r, v[:, :, 2:]], axis=-1)
+    else:
+        raise ValueError(variant)
+    parts = [head, f_cluster, f_center]
+    if variant == "radius_height":
+        h = rh(v[:, :, 2:3].max(axis=1, keepdims=True) - v[:, :, 2:3].min(axis=1, keepdims=True))
+        parts.append(np.broadcast_to(h, (P, T, 1)).astype(f32))
+    if with_distance:
+        src = head if variant == "old" else v
+        parts.append(rh(np.sqrt((src[:, :, :3] * src[:, :, :3]).sum(axis=2, dtype=f32), dtype=f32))[..., None])
+    feats = np.concatenate(parts, axis=-1).astype(f32)
+    mask = paddings_indicator(num, T).astype(f32)[..., None]
+    return (feats * mask).astype(f16)

@@ -10,7 +10,31 @@ from lyft3d_b200 import synth
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-6   # BASELINE.json north_star: pillar features within 1e-6 relative
-ATOL = 1e-5   # fp32 ulp of a +-50 m coordinate is 3.8e-6: differences x - mean inherit it
+ATOL = 4e-6   # one float32 ulp of a +-50 m coordinate (3.8e-6): f_cluster = x - mean inherits it, because the
+              # order of the float32 sum over T is the one freedom of this op (torch's own CPU and CUDA sums differ
+              # by the same amount).  _report() below measures what is actually achieved.
+
+
+def _report(tag, out, ref, voxels, num, variant):
+    """Achieved error of a decoration: channels that do not depend on the pillar mean must be BIT-EXACT; the
+    f_cluster channels are reported as max relative error where |ref| > 1e-3 and as max absolute error in
+    float32 ulps of the pillar's largest coordinate, and must stay within 1 such ulp."""
+    k = 4 if variant in ("pfn", "old") else 3
+    cl = [k, k + 1, k + 2]
+    rest = [c for c in range(ref.shape[2]) if c not in cl]
+    assert np.array_equal(out[..., rest].view(np.uint32), ref[..., rest].view(np.uint32)), "mean-independent channels differ"
+    mask = np.arange(ref.shape[1])[None, :] < np.asarray(num)[:, None]
+    a, b = out[..., cl][mask], ref[..., cl][mask]
+    big = np.abs(voxels[..., :3]).max(axis=(1, 2))
+    ulp = np.repeat(np.spacing(big.astype(np.float32))[:, None], ref.shape[1], axis=1)[mask][:, None]
+    err = np.abs(a - b)
+    sel = np.abs(b) > 1e-3
+    rel = float((err[sel] / np.abs(b[sel])).max()) if sel.any() else 0.0
+    ulps = float((err / ulp).max())
+    print("%s: f_cluster max rel err (|ref| > 1e-3) %.3g, max abs err %.3g = %.2f ulp of the pillar coordinate, "
+          "%.4f of the values bit-identical" % (tag, rel, float(err.max()), ulps, float((a == b).mean())))
+    assert ulps <= 1.0
+    return rel, ulps
 
 
 @pytest.fixture(scope="module")
@@ -45,6 +69,7 @@ def test_decorate_vs_reference_outputs(pp, g, variant, wd):
     ref = g["dec_%s_%d" % (variant, int(wd))]
     assert out.shape == ref.shape
     np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+    _report("decorate %s wd=%d vs the reference's own output" % (variant, wd), out, ref, g["voxels"], g["num_points"], variant)
     mask = np.arange(ref.shape[1])[None, :] < g["num_points"][:, None]
     assert np.all(out[~mask] == 0)
     # channels that are plain copies are bit-exact
@@ -78,6 +103,7 @@ def test_decorate_large_vs_oracle(pp, cloud11):
     ref = po.decorate(v, n, coors, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE)
     assert out.shape == (30000, 60, 9)
     np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+    _report("decorate 30000 pillars of the 11-sweep cloud vs the oracle", out, ref, v, n, "pfn")
 
 
 def test_decorate_generic_feature_count(pp):
