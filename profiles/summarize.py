@@ -3,6 +3,9 @@
 
   python profiles/summarize.py launches gpurun_out/launches_X.csv  > profiles/X_launches.txt
   python profiles/summarize.py full gpurun_out/prof_X.ncu-rep      > profiles/X_full.txt
+  python profiles/summarize.py traffic gpurun_out/prof_X.ncu-rep   > profiles/r02_traffic.json
+      (dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of every stage, stamped with
+       the sha of the kernel sources it was captured from: bench.py drops `roofline.traffic` when they differ)
 """
 import collections
 import csv
@@ -63,5 +66,42 @@ def full(path):
                 print("   %-72s %16s %s" % (k, d[idx[k]], units[idx[k]]))
 
 
+def _to_bytes(val, unit):
+    v = float(val.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+
+
+def traffic(path):
+    import datetime
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    per = collections.OrderedDict()
+    for d in data:
+        name = d[idx["Kernel Name"]].split("(")[0]
+        b = sum(_to_bytes(d[idx[k]], units[idx[k]]) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        per.setdefault(name, []).append(b)
+    first = {k: v[0] for k, v in per.items()}
+
+    def pick(sub):
+        return [(k, v) for k, v in first.items() if sub in k]
+    stages = {
+        "scatter": {"kernel": "pillar_canvas_q_kernel", "dram_bytes_per_launch": int(sum(v for _, v in pick("pillar_canvas_q")))},
+        "pillarize": {"kernel": "vx_bins_kernel<decorate>", "dram_bytes_per_launch": int(sum(v for _, v in pick("vx_bins_kernel<1")))},
+        "bev": {"kernel": "bev_hist_kernel + bev_finalize_flat4_kernel",
+                "dram_bytes_per_launch": int(sum(v for _, v in pick("bev_hist") + pick("bev_finalize")))},
+    }
+    print(json.dumps({"frames_per_step": 128, "source_sha16": bench.source_sha(),
+                      "captured": datetime.date.today().isoformat(),
+                      "source": "ncu --set full --clock-control none on `python bench.py --steps 1 --warmup 3 --no-e2e "
+                                "--no-cpu-baseline --no-other-configs --no-verify --no-eager-ref --serial`",
+                      "stages": stages}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])

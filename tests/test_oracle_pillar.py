@@ -51,3 +51,23 @@ def test_merge_batch_coords():
     b = np.array([[0, 5, 6]], np.int32)
     m = po.merge_batch_coords([a, b])
     assert m.tolist() == [[0, 0, 1, 2], [0, 0, 3, 4], [1, 0, 5, 6]] and m.dtype == np.int32
+
+
+def test_eager_torch_restatement_equals_reference_outputs(golden_dir):
+    """oracle/pillar_torch_ref.py (the reference's GPU op chain, timed by bench.py as `reference_gpu_eager`) gives
+    the outputs of the reference's own classes bit for bit when run on the CPU like they were."""
+    import os
+    import torch
+    from lyft3d_b200 import synth
+    from oracle import pillar_torch_ref as tr
+    g = np.load(os.path.join(golden_dir, "ref_pillar_decorate.npz"))
+    vx, vy = synth.PILLAR_VOXEL_SIZE[0], synth.PILLAR_VOXEL_SIZE[1]
+    xo, yo = vx / 2 + synth.PILLAR_RANGE[0], vy / 2 + synth.PILLAR_RANGE[1]
+    for wd in (False, True):
+        out = tr.decorate(torch.from_numpy(g["voxels"].copy()), torch.from_numpy(g["num_points"]), torch.from_numpy(g["coors"]),
+                          vx, vy, xo, yo, with_distance=wd).numpy()
+        assert np.array_equal(out.view(np.uint32), g["dec_pfn_%d" % int(wd)].view(np.uint32))
+    s = np.load(os.path.join(golden_dir, "ref_scatter.npz"))
+    B, C, ny, nx = (int(v) for v in s["shape"])
+    canvas = tr.scatter(torch.from_numpy(s["feats"]), torch.from_numpy(s["coords"]), B, ny, nx).numpy()
+    assert np.array_equal(canvas.view(np.uint32), s["canvas"].view(np.uint32))
