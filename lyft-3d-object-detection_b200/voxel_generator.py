@@ -116,6 +116,42 @@ def voxelize_frames(points, frame_offsets, voxel_size, coors_range, max_points, 
     return voxels, coords, num, vnum
 
 
+def voxelize_concat_frames(points, frame_offsets, voxel_size, coors_range, max_points, max_voxels,
+                           overflow="continue", capacity=None, handle=None):
+    """Batched voxelization straight into the layout ``merge_second_batch`` produces
+    (second/second/data/preprocess.py:21-55; lv_voxelize_concat): points (N_total, C) float32 CUDA
+    tensor, frame_offsets int64 (F+1).  Returns CUDA tensors voxels (sum V, T, C), coordinates
+    (sum V, 4) [b, z, y, x], num_points_per_voxel (sum V) and voxel_num (F).  One host read (the
+    total), like the reference's ``voxels.shape[0]`` (preprocess.py:310)."""
+    import torch
+    if overflow not in ("continue", "break"):
+        raise ValueError("overflow must be 'continue' or 'break'")
+    if not (_is_cuda_tensor(points) and points.dim() == 2 and points.dtype == torch.float32):
+        raise ValueError("points must be a (N, C) float32 CUDA tensor")
+    lib = nat.load()
+    pts = points.contiguous()
+    offs = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+    F = offs.shape[0] - 1
+    V, T, C = int(max_voxels), int(max_points), pts.shape[1]
+    cap = int(capacity if capacity is not None else F * V)
+    dev = pts.device
+    cfg = _make_config(voxel_size, coors_range, T, V, C, overflow, False)
+    voxels = torch.empty((cap, T, C), dtype=torch.float32, device=dev)
+    coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((cap,), dtype=torch.int32, device=dev)
+    vnum = torch.empty((F,), dtype=torch.int32, device=dev)
+    voff = torch.zeros((F + 1,), dtype=torch.int64, device=dev)
+    h = handle or nat.get_handle(dev.index)
+    with torch.cuda.device(dev):
+        nat.check(lib.lv_voxelize_concat(h.ptr, ctypes.byref(cfg), pts.data_ptr(), F, offs.ctypes.data, cap,
+                                         voxels.data_ptr(), coords.data_ptr(), num.data_ptr(), vnum.data_ptr(),
+                                         voff.data_ptr(), nat.current_stream_ptr(dev)))
+    total = int(voff[F].item()) if F > 0 else 0
+    if total > cap:
+        raise nat.LyftVoxelError(nat.LV_E_INVALID, "voxel capacity %d exceeded (%d rows)" % (cap, total))
+    return voxels[:total], coords[:total], num[:total], vnum
+
+
 def voxelize_host_single(points, voxel_size, coors_range, max_points, max_voxels, overflow="continue",
                          padded=False, block_filter=None, handle=None):
     """One cloud, host numpy in and out, through lv_voxelize_host_begin / _fetch: the arrays that come

@@ -215,3 +215,33 @@ def run_bev_closures(points, shape, voxel_size, z_offset):
     bev = fn["normalize_voxel_intensities"](raw)
     bev_im = np.round(bev * 255).astype(np.uint8)
     return raw, bev, bev_im
+
+
+def _function_source(path, name):
+    """Source of the top-level ``def name(`` of the reference file `path`, unchanged."""
+    with open(path) as f:
+        lines = f.readlines()
+    start = next(i for i, l in enumerate(lines) if l.startswith("def %s(" % name))
+    end = start + 1
+    while end < len(lines) and (not lines[end].strip() or lines[end][0] in " \t"):
+        end += 1
+    return "".join(lines[start:end])
+
+
+def load_collate_functions():
+    """The reference's own batch assembly: ``merge_second_batch`` / ``merge_second_batch_multigpu``
+    (second/second/data/preprocess.py:21-88) and ``example_convert_to_torch``
+    (second/second/pytorch/train.py:34-62).  Neither module imports here (skimage, spconv, fire ...),
+    so the three function bodies are read from the reference files and executed unchanged.
+    Returns a dict name -> function."""
+    from collections import defaultdict
+
+    import numpy as np
+    import torch
+    pre = os.path.join(REF, "second", "second", "data", "preprocess.py")
+    trn = os.path.join(REF, "second", "second", "pytorch", "train.py")
+    ns = {"np": np, "defaultdict": defaultdict, "torch": torch}
+    for path, name in ((pre, "merge_second_batch"), (pre, "merge_second_batch_multigpu"),
+                       (trn, "example_convert_to_torch")):
+        exec(compile(_function_source(path, name), path, "exec"), ns)
+    return {n: ns[n] for n in ("merge_second_batch", "merge_second_batch_multigpu", "example_convert_to_torch")}
