@@ -173,6 +173,10 @@ int lv_set_option(lv_handle* h, const char* name, int64_t value) {
     h->vox_list_path = value;
     return LV_OK;
   }
+  if (strcmp(name, "vox_fused_prologue") == 0) {
+    h->vox_fused_prologue = value;
+    return LV_OK;
+  }
   if (strcmp(name, "vox_rows_waves") == 0) {
     h->vox_rows_waves = value;
     return LV_OK;

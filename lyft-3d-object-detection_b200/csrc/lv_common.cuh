@@ -80,6 +80,9 @@ struct lv_handle {
                                       // 128 pillar frames) - scattered 4-byte DSMEM accesses run at ~0.5 per cycle and SM
   int64_t vox_list_path = 0;          // 1: grids with a small dense map run the three-kernel list path (lv_voxel_list.cuh).  Off by
                                       // default: bit-identical but measured slower (1.03 vs 0.67 ms per 128 pillar frames)
+  int64_t vox_fused_prologue = 0;     // 1: frames of <= 64 chunks run K1-K5 as ONE kernel (vx_fused_kernel: per-frame arrival counters,
+                                      // look-back and polling instead of kernel boundaries).  Off by default: bit-identical, but measured
+                                      // slower (0.724 vs 0.671 ms per 128 pillar frames; see the kernel's header in lv_voxel.cu)
   int64_t vox_rows_waves = 0;         // CTAs of vl_rows_kernel per resident slot (0 = 4)
   int64_t canvas_variant = 0;         // 0 = auto (pillar_canvas_q_kernel when the shape allows), 1 = pillar_canvas_kernel (A/B)
 
@@ -94,7 +97,7 @@ struct lv_handle {
   // voxelizer
   lv_buffer vox_map;                  // i32 [frames_in_flight][grid cells], kept all-INT_MAX between calls
   lv_buffer vox_cell, vox_aux, vox_keys[2], vox_vals[2], vox_hist, vox_chunk, vox_frame_state;
-  lv_buffer vox_row_base, vox_vrec;
+  lv_buffer vox_row_base, vox_vrec, vox_bin_start, vox_fused;
   lv_mirror vox_frame_offsets, vox_chunk_table, vox_chunk_frame;
   lv_buffer vox_stage_points, vox_stage_out[4];
   int32_t vox_host_frames = 0;        // frames held by the staging buffers since the last lv_voxelize_host_begin
@@ -117,7 +120,7 @@ inline std::vector<lv_buffer*> lv_all_buffers(lv_handle* h) {
           &h->bev_stage_out[0], &h->bev_stage_out[1], &h->bev_stage_out[2], &h->bev_stage_out[3], &h->bev_stage_out[4],
           &h->bev_stage_map, &h->draw_offsets.dev, &h->draw_recs, &h->draw_stage[0], &h->draw_stage[1], &h->draw_stage[2],
           &h->vox_map, &h->vox_cell, &h->vox_aux, &h->vox_keys[0], &h->vox_keys[1], &h->vox_vals[0],
-          &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state, &h->vox_row_base, &h->vox_vrec,
+          &h->vox_vals[1], &h->vox_hist, &h->vox_chunk, &h->vox_frame_state, &h->vox_row_base, &h->vox_vrec, &h->vox_bin_start, &h->vox_fused,
           &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_chunk_frame.dev, &h->vox_stage_points, &h->vox_stage_out[0],
           &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3], &h->flt_ranges, &h->flt_dst, &h->flt_tmp[0], &h->flt_tmp[1],
           &h->flt_tmp[2], &h->flt_tmp[3], &h->pil_map, &h->ing_offsets.dev,

@@ -86,6 +86,9 @@ struct VoxParams {
   int32_t* hist;               // [chunks * n_bins], per frame laid out [bin][chunk]
   int32_t* frame_cut;          // [frames] break cut-off (local index)
   int32_t* frame_kept;         // [frames] kept points
+  int32_t* bin_start;          // [frames][n_bins + 1] first list position of every bin of a frame (+ the kept total)
+  unsigned* frame_sync;        // [frames][2] arrival counters of the fused prologue (all zero between calls)
+  int* err;                    // device flag: a bounded spin of the fused prologue gave up
   // outputs
   float* voxels; int32_t* coords; int32_t* num_points; int32_t* voxel_num;
   int64_t* row_base;           // [F+1] first output row of every frame (concat: prefix of voxel_num)
@@ -387,6 +390,11 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scan_hist_kernel(VoxParams p) {
     p.frame_kept[fl] = total;
     if (nch == 0) p.voxel_num[f] = 0;  // a frame without points never ran K2
   }
+  // first list position of every bin (what K6 reads), the kept total behind them
+  __syncthreads();
+  int32_t* bstart = p.bin_start + (int64_t)fl * (p.n_bins + 1);
+  for (int d = threadIdx.x; d < p.n_bins; d += VX_THREADS) bstart[d] = nch > 0 ? p.hist[(int64_t)cb * p.n_bins + (int64_t)d * nch] : 0;
+  if (threadIdx.x == 0) bstart[p.n_bins] = total;
 }
 
 // ---------------------------------------------------------------- K5: stable multi-split into bins
@@ -455,6 +463,325 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p) {
     if (key[r] == VX_DROPPED) continue;
     const int64_t pos = out0 + mycnt[key[r] >> p.low_bits] + rnk[r];
     p.keys[pos] = key[r];
+    p.vals[pos] = base + r * 32 + lane;
+  }
+}
+
+// ---------------------------------------------------------------- KX: K1-K5 in ONE launch (frames of <= 64 chunks)
+// One CTA keeps its 2,048 points in registers from the coordinate rule to the final multi-split position; what the
+// kernel boundaries of K1-K5 ordered is ordered by device-side mechanisms instead:
+//   * frame barrier 1 (arrival counter per frame) between the atomicMin bids and the creator test,
+//   * the decoupled look-back of K2 for the voxel ids,
+//   * polling: a non-creator spins on first[cell] until its creator - always an EARLIER point, i.e. the same or an
+//     earlier chunk - has replaced the point index by ~rank,
+//   * frame barrier 2 between the publication of the per-chunk bin counts and their prefix; the [bin][chunk]
+//     table of a frame (<= 64 chunks) is read by every CTA of the frame instead of being scanned by a kernel.
+// Needs every CTA of a frame resident at the same time (the host checks chunks-per-frame against the occupancy of
+// the kernel); CTAs are dispatched in blockIdx order, so the earliest unfinished frame always has all of its CTAs
+// on the machine - the same forward-progress assumption as the look-back.  cell[] and key0[] are never written.
+// Spins are bounded (~1 s) and raise p.err instead of hanging the GPU.
+// OPT-IN (lv_set_option "vox_fused_prologue" 1): bit-identical to K1-K5 (tests/test_gpu_voxel_fused.py), but measured
+// SLOWER on 128 C5 frames - pillarize stage 0.724 vs 0.671 ms; ncu: 228 us against 168 us for the five kernels.  43 %
+// of its stall samples sit in the frame barriers: every phase keeps the latency it had as a kernel of its own (a
+// chunk's loads and bids take ~15 us under load whether or not a kernel boundary follows), while the CTA now holds
+// 48 registers x 256 threads through all of them (5 CTAs/SM instead of 8) and waits for the slowest chunk of its
+// frame twice.  Re-reading cell[] / first[] / key0[] between kernels costs little: they are L2 hits.
+#ifndef VX_FUSED_MINB
+#define VX_FUSED_MINB 5
+#endif
+#define VX_FUSED_MAX_CHUNKS 64
+#define VX_FUSED_MAX_BINS 1024
+#define VX_FUSED_BINS_PER_THREAD (VX_FUSED_MAX_BINS / VX_THREADS)
+
+__device__ __forceinline__ int vx_ld_relaxed(const int32_t* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void vx_st_relaxed(int32_t* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned vx_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// every CTA of the frame arrives (release: barrier, fence, atomic) and waits for `target` arrivals (acquire)
+__device__ __forceinline__ void vx_frame_barrier(unsigned* ctr, unsigned target, int* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const long long t0 = clock64();
+    while (vx_ld_acquire(ctr) < target) {
+      __nanosleep(64);
+      if (clock64() - t0 > (1ll << 31)) {
+        *err = 1;
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <bool C4>
+__global__ void __launch_bounds__(VX_THREADS, VX_FUSED_MINB) vx_fused_kernel(VoxParams p) {
+  extern __shared__ __align__(128) int xsm[];    // the TMA tile [VX_CHUNK][C], then cnt[8][D] | binbase[D] | table [D][chunks]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int sw[VX_WARPS];
+  __shared__ int s_excl, s_cut;
+  const ChunkLoc L = vx_locate(p);
+  const int D = p.n_bins;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = lv_lanemask_lt();
+  int32_t* map = p.map + (int64_t)L.fl * p.G;
+  unsigned* sync = p.frame_sync + 2 * L.fl;
+  const float* tile = reinterpret_cast<const float*>(xsm);
+  const float* src = p.pts + (L.start + (int64_t)L.c * VX_CHUNK) * p.C;
+  const bool staged = p.tma_bytes != 0 && (L.c + 1) * VX_CHUNK <= L.n && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  if (threadIdx.x == 0 && staged) {
+    lv_mbar_init(&bar, 1);
+    lv_mbar_init_fence();
+    lv_mbar_expect_tx(&bar, p.tma_bytes);
+    lv_tma_load_1d(xsm, src, p.tma_bytes, &bar);
+  }
+  if (staged) {
+    __syncthreads();  // the barrier is initialised
+    lv_mbar_wait(&bar, 0);
+  }
+  // ---- K1: cells (kept in registers) and the bids for first[]
+  const int base = L.c * VX_CHUNK + warp * (32 * VX_ITEMS);   // (warp, round, lane) order is point order
+  int cell[VX_ITEMS];
+#pragma unroll
+  for (int r = 0; r < VX_ITEMS; ++r) {
+    const int ti = warp * (32 * VX_ITEMS) + r * 32 + lane;
+    const int li = base + r * 32 + lane;
+    cell[r] = -1;
+    if (li < L.n) {
+      const int64_t gi = L.start + li;
+      float x, y, z;
+      if (C4) {
+        float4 v;
+        if (staged) v = reinterpret_cast<const float4*>(tile)[ti];
+        else v = __ldg(reinterpret_cast<const float4*>(p.pts) + gi);
+        x = v.x; y = v.y; z = v.z;
+      } else if (staged) {
+        const float* q = tile + ti * p.C;
+        x = q[0]; y = q[1]; z = q[2];
+      } else {
+        const float* q = p.pts + gi * p.C;
+        x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
+      }
+      // simplevis.py:38-42: c = floor((p - lo) / vs) in float32, bounds on the float
+      const float cx = floorf(__fdiv_rn(__fsub_rn(x, p.lo[0]), p.vs[0]));
+      const float cy = floorf(__fdiv_rn(__fsub_rn(y, p.lo[1]), p.vs[1]));
+      const float cz = floorf(__fdiv_rn(__fsub_rn(z, p.lo[2]), p.vs[2]));
+      if (cx >= 0.f && cx < (float)p.grid[0] && cy >= 0.f && cy < (float)p.grid[1] && cz >= 0.f &&
+          cz < (float)p.grid[2])
+        cell[r] = ((int)cz * p.grid[1] + (int)cy) * p.grid[0] + (int)cx;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < VX_ITEMS; ++r) {
+    const unsigned peers = __match_any_sync(0xffffffffu, cell[r]);
+    if (cell[r] >= 0 && lane == __ffs(peers) - 1) atomicMin(map + cell[r], base + r * 32 + lane);
+  }
+  vx_frame_barrier(sync, (unsigned)L.nchunks, p.err);      // every bid of the frame has landed
+  // the tile is consumed: its shared memory becomes the per-warp bin counters
+  int* cnt = xsm;                     // [8][D]
+  int* binbase = xsm + VX_WARPS * D;  // [D]
+  for (int i = threadIdx.x; i < VX_WARPS * D; i += VX_THREADS) cnt[i] = 0;
+
+  // ---- K2: creators, voxel ids in first-come order
+  unsigned bal[VX_ITEMS];
+  int vid[VX_ITEMS];              // first[cell] as read (a point index, or ~id once the creator has ranked), then the id
+  int wc = 0;
+#pragma unroll
+  for (int r = 0; r < VX_ITEMS; ++r) vid[r] = cell[r] >= 0 ? vx_ld_relaxed(map + cell[r]) : -1;
+#pragma unroll
+  for (int r = 0; r < VX_ITEMS; ++r) {
+    bal[r] = __ballot_sync(0xffffffffu, cell[r] >= 0 && vid[r] == base + r * 32 + lane);
+    wc += __popc(bal[r]);
+  }
+  if (lane == 0) sw[warp] = wc;
+  __syncthreads();
+  int woff = 0, agg = 0;
+#pragma unroll
+  for (int w = 0; w < VX_WARPS; ++w) {
+    if (w < warp) woff += sw[w];
+    agg += sw[w];
+  }
+  if (warp == 0) {
+    unsigned long long* st = p.chunk_state + blockIdx.x;
+    int excl = 0;
+    if (L.c == 0) {
+      if (lane == 0) vx_st_state(st, VX_FLAG_PREFIX | (unsigned)agg);
+    } else {
+      if (lane == 0) vx_st_state(st, VX_FLAG_AGG | (unsigned)agg);
+      int look = L.c - 1;
+      while (true) {
+        const int idx = look - lane;
+        unsigned long long v = VX_FLAG_PREFIX;
+        if (idx >= 0) {
+          do { v = vx_ld_state(st - (L.c - idx)); } while ((v >> 62) == 0);
+        }
+        const unsigned is_prefix = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int first_p = __ffs(is_prefix) - 1;
+        int contrib = (first_p < 0 || lane <= first_p) ? (int)(unsigned)(v & 0xffffffffull) : 0;
+        if (idx < 0) contrib = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (first_p >= 0) break;
+        look -= 32;
+      }
+      if (lane == 0) vx_st_state(st, VX_FLAG_PREFIX | (unsigned)(excl + agg));
+    }
+    if (lane == 0) {
+      s_excl = excl;
+      // `break` (simplevis.py:48-49): the creator of id V cuts the frame.  It lies in an earlier chunk (every
+      // point here is past it), in this chunk (it writes s_cut below), or further on / nowhere.
+      s_cut = (p.overflow == LV_OVERFLOW_BREAK && excl > p.V) ? 0 : 0x7fffffff;
+      if (L.c == L.nchunks - 1) {
+        const int total = excl + agg;
+        p.voxel_num[L.f] = total < p.V ? total : p.V;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    int run = s_excl + woff;
+    int32_t* ccell = p.creator_cell + (L.start - p.pt_lo);
+#pragma unroll
+    for (int r = 0; r < VX_ITEMS; ++r) {
+      if ((bal[r] >> lane) & 1u) {
+        const int rank = run + __popc(bal[r] & lt);
+        vid[r] = ~rank;
+        vx_st_relaxed(map + cell[r], ~rank);  // voxel id, stored negative so it never equals a point index
+        ccell[rank] = cell[r];                // rank < number of points of the frame
+        if (rank == p.V && p.overflow == LV_OVERFLOW_BREAK) s_cut = base + r * 32 + lane;
+      }
+      run += __popc(bal[r]);
+    }
+  }
+  __syncthreads();
+  // ---- K3: voxel id of every other point (its creator is an earlier point: poll until the id is there)
+  const int cut = s_cut;
+#pragma unroll
+  for (int r = 0; r < VX_ITEMS; ++r) {
+    if (cell[r] >= 0 && vid[r] >= 0) {
+      const long long t0 = clock64();
+      int v;
+      while ((v = vx_ld_relaxed(map + cell[r])) >= 0) {
+        __nanosleep(32);
+        if (clock64() - t0 > (1ll << 31)) {
+          *p.err = 2;
+          v = -1;
+          break;
+        }
+      }
+      vid[r] = v;
+    }
+    vid[r] = ~vid[r];   // (cell < 0: ~(-1) = 0, dropped below)
+    if (cell[r] < 0 || vid[r] >= p.V || base + r * 32 + lane >= cut) vid[r] = -1;   // dropped
+  }
+  // ---- K5 (first half): stable rank inside (warp, bin)
+  int* mycnt = cnt + warp * D;
+  int rnk[VX_ITEMS];
+#pragma unroll
+  for (int r = 0; r < VX_ITEMS; ++r) {
+    const unsigned digit = vid[r] < 0 ? 0xffffffffu : ((unsigned)vid[r] >> p.low_bits);
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    const int leader = __ffs(peers) - 1;
+    int old = 0;
+    if (vid[r] >= 0 && lane == leader) {
+      old = mycnt[digit];
+      mycnt[digit] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rnk[r] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  // per-bin counts of the chunk -> the frame's [bin][chunk] table; counters become offsets inside the CTA
+  int32_t* tab = p.hist + (int64_t)(__ldg(p.frame_chunk + L.f) - p.chunk_lo) * D;
+  for (int d = threadIdx.x; d < D; d += VX_THREADS) {
+    int off = 0;
+#pragma unroll
+    for (int w = 0; w < VX_WARPS; ++w) {
+      const int t = cnt[w * D + d];
+      cnt[w * D + d] = off;
+      off += t;
+    }
+    tab[(int64_t)d * L.nchunks + L.c] = off;
+  }
+  vx_frame_barrier(sync + 1, (unsigned)L.nchunks, p.err);  // the table of the frame is complete; first[] is read out
+  // touched-cell reset and the look-back descriptor back to "invalid": nobody of the frame needs them any more
+#pragma unroll
+  for (int r = 0; r < VX_ITEMS; ++r)
+    if ((bal[r] >> lane) & 1u) map[cell[r]] = VX_EMPTY;
+  if (threadIdx.x == 0) p.chunk_state[blockIdx.x] = 0ull;
+  // ---- K4: this chunk's base inside every bin = bin start + counts of the earlier chunks.  The frame's table
+  //      comes to shared memory in one batch of independent coalesced loads; thread t owns bins [t*PER, (t+1)*PER)
+  {
+    int* stab = binbase + D;        // [D][nchunks]
+    const int n_tab = D * L.nchunks;
+    for (int i = threadIdx.x; i < n_tab; i += VX_THREADS) stab[i] = __ldcg(tab + i);
+    __syncthreads();
+    const int PER = (D + VX_THREADS - 1) / VX_THREADS;   // <= VX_FUSED_BINS_PER_THREAD
+    int tot[VX_FUSED_BINS_PER_THREAD], below[VX_FUSED_BINS_PER_THREAD];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < VX_FUSED_BINS_PER_THREAD; ++j) {
+      tot[j] = 0; below[j] = 0;
+      const int d = threadIdx.x * PER + j;
+      if (j < PER && d < D) {
+        const int* row = stab + d * L.nchunks;
+        for (int c = 0; c < L.nchunks; ++c) {
+          const int t = row[c];
+          tot[j] += t;
+          if (c < L.c) below[j] += t;
+        }
+      }
+      mine += tot[j];
+    }
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) sw[warp] = inc;
+    __syncthreads();
+    int wbase = 0, kept = 0;
+#pragma unroll
+    for (int w = 0; w < VX_WARPS; ++w) {
+      if (w < warp) wbase += sw[w];
+      kept += sw[w];
+    }
+    int run = wbase + inc - mine;
+    int32_t* bstart = p.bin_start + (int64_t)L.fl * (D + 1);
+#pragma unroll
+    for (int j = 0; j < VX_FUSED_BINS_PER_THREAD; ++j) {
+      const int d = threadIdx.x * PER + j;
+      if (j < PER && d < D) {
+        binbase[d] = run + below[j];
+        if (L.c == 0) bstart[d] = run;
+        run += tot[j];
+      }
+    }
+    if (L.c == 0 && threadIdx.x == 0) bstart[D] = kept;
+  }
+  __syncthreads();
+  // ---- K5 (second half): the kept points grouped by bin, in point order
+  const int64_t out0 = L.start - p.pt_lo;
+#pragma unroll
+  for (int r = 0; r < VX_ITEMS; ++r) {
+    if (vid[r] < 0) continue;
+    const unsigned digit = (unsigned)vid[r] >> p.low_bits;
+    const int64_t pos = out0 + binbase[digit] + mycnt[digit] + rnk[r];
+    p.keys[pos] = (unsigned)vid[r];
     p.vals[pos] = base + r * 32 + lane;
   }
 }
@@ -665,7 +992,10 @@ __global__ void __launch_bounds__(VF_THREADS, 1) vx_frame_kernel(VoxParams p, in
       if (d < D) dbase[d] = carry + inc - v;
       carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (crank == 0 && lane == 0) p.frame_kept[fl] = carry;
+    if (crank == 0 && lane == 0) {
+      p.frame_kept[fl] = carry;
+      p.bin_start[(int64_t)fl * (D + 1) + D] = carry;
+    }
   }
   __syncthreads();
   {
@@ -676,7 +1006,8 @@ __global__ void __launch_bounds__(VF_THREADS, 1) vx_frame_kernel(VoxParams p, in
       int below = dbase[d];
       for (int c = 0; c < crank; ++c) below += ctot[c * D + d];
       for (int w = 0; w < VF_WARPS; ++w) cnt[w * D + d] += below;
-      if (crank == 0 && nch > 0) tab[(int64_t)d * nch] = dbase[d];   // what K6 reads: first position of bin d
+      if (crank == 0) p.bin_start[(int64_t)fl * (D + 1) + d] = dbase[d];   // what K6 reads: first position of bin d
+      if (crank == 0 && nch > 0) tab[(int64_t)d * nch] = dbase[d];
     }
   }
   __syncthreads();
@@ -725,6 +1056,7 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : VX_BINS_M
   const long long tp0 = clock64();
 #endif
   const int vnum = p.voxel_num[f];
+  if (b == 0 && threadIdx.x < 2 && p.frame_sync) p.frame_sync[2 * fl + threadIdx.x] = 0u;   // fused prologue: counters back to zero
   if ((b << p.low_bits) >= vnum && b != 0) return;  // bin beyond the last voxel: nothing to do
   // first output row of the frame: prefix of voxel_num over the earlier frames of the batch
   if (warp == 0) {
@@ -752,9 +1084,7 @@ __global__ void __launch_bounds__(VX_THREADS, MODE == VX_OUT_PFN ? 3 : VX_BINS_M
   const int cb = __ldg(p.frame_chunk + f) - p.chunk_lo;
   const int nch = __ldg(p.frame_chunk + f + 1) - __ldg(p.frame_chunk + f);
   if (nv <= 0 || nch == 0) return;  // (uniform across the CTA)
-  const int32_t* tab = p.hist + (int64_t)cb * p.n_bins;
-  const int seg_lo = tab[(int64_t)b * nch];
-  const int seg_hi = (b + 1 < p.n_bins) ? tab[(int64_t)(b + 1) * nch] : p.frame_kept[fl];
+  const int seg_lo = p.bin_start[(int64_t)fl * (p.n_bins + 1) + b], seg_hi = p.bin_start[(int64_t)fl * (p.n_bins + 1) + b + 1];
   const int64_t fstart = __ldg(p.frame_off + f);
   const uint32_t* keys = p.keys + (fstart - p.pt_lo);
   const int32_t* vals = p.vals + (fstart - p.pt_lo);
@@ -1305,6 +1635,7 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     LV_CHECK(vx_set_smem(vl_cells_kernel<true>, p.tma_bytes));
   }
 
+  const bool fused_ok = h->vox_fused_prologue != 0 && !list_path && n_bins <= VX_FUSED_MAX_BINS;
   int f0 = 0;
   while (f0 < n_frames) {
     int f1 = f0 + 1;
@@ -1369,6 +1700,50 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     LV_CHECK(h->vox_chunk.ensure((size_t)(nchunks + 1) * 8, stream));            // look-back descriptors
     LV_CHECK(h->vox_hist.ensure((size_t)(nchunks + 1) * n_bins * 4, stream));
     LV_CHECK(h->vox_frame_state.ensure((size_t)nf * 2 * 4, stream));
+    LV_CHECK(h->vox_bin_start.ensure((size_t)nf * (n_bins + 1) * 4, stream));
+    p.bin_start = h->vox_bin_start.as<int32_t>();
+    p.frame_sync = nullptr;
+    // fused prologue: every CTA of a frame must be resident at once, its table must fit the CTA's shared memory
+    bool fused = false;
+    if (fused_ok && frame_cs == 0 && nchunks > 0) {
+      int max_ch = 0, min_ch = 1 << 30;
+      for (int f = f0; f < f1; ++f) {
+        const int ch = frame_chunk[f + 1] - frame_chunk[f];
+        if (ch > max_ch) max_ch = ch;
+        if (ch < min_ch) min_ch = ch;
+      }
+      size_t smem_fused = ((size_t)(VX_WARPS + 1 + max_ch) * n_bins) * 4;
+      if (smem_fused < p.tma_bytes) smem_fused = p.tma_bytes;
+      if (min_ch > 0 && max_ch <= VX_FUSED_MAX_CHUNKS && smem_fused <= 64 * 1024) {
+        int per_sm = 0;
+        if (c4) {
+          LV_CHECK(vx_set_smem(vx_fused_kernel<true>, smem_fused));
+          LV_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vx_fused_kernel<true>, VX_THREADS, smem_fused));
+        } else {
+          LV_CHECK(vx_set_smem(vx_fused_kernel<false>, smem_fused));
+          LV_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vx_fused_kernel<false>, VX_THREADS, smem_fused));
+        }
+        if ((int64_t)per_sm * h->num_sms >= 2 * (int64_t)max_ch) {   // a factor two of slack for co-running kernels
+          fused = true;
+          // [chunks] look-back descriptors | [frames][2] arrival counters | error flag: all zero between calls
+          const size_t st_bytes = lv_align_up((size_t)(nchunks + 1) * 8, 16);
+          LV_CHECK(h->vox_fused.ensure(st_bytes + (size_t)nf * 8 + 16, stream, 0));
+          p.map = h->vox_map.as<int32_t>();
+          p.keys = h->vox_keys[0].as<uint32_t>();
+          p.vals = h->vox_vals[0].as<int32_t>();
+          p.creator_cell = h->vox_aux.as<int32_t>();
+          p.hist = h->vox_hist.as<int32_t>();
+          p.chunk_state = h->vox_fused.as<unsigned long long>();
+          p.frame_sync = reinterpret_cast<unsigned*>(h->vox_fused.as<unsigned char>() + st_bytes);
+          p.err = reinterpret_cast<int*>(p.frame_sync + (size_t)nf * 2);
+          p.frame_cut = h->vox_frame_state.as<int32_t>();
+          p.frame_kept = p.frame_cut + nf;
+          if (c4) vx_fused_kernel<true><<<nchunks, VX_THREADS, smem_fused, stream>>>(p);
+          else vx_fused_kernel<false><<<nchunks, VX_THREADS, smem_fused, stream>>>(p);
+          LV_LAUNCH_CHECK(h);
+        }
+      }
+    }
     p.map = h->vox_map.as<int32_t>();
     p.cell = h->vox_cell.as<int32_t>();
     p.key0 = h->vox_cell.as<uint32_t>() + (npts + 1);
@@ -1380,7 +1755,9 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     p.frame_cut = h->vox_frame_state.as<int32_t>();
     p.frame_kept = p.frame_cut + nf;
 
-    if (frame_cs > 0) {
+    if (fused) {
+      // K1-K5 ran as one kernel above
+    } else if (frame_cs > 0) {
       // small grid: K1-K5 of every frame inside one thread-block cluster, the dense map in distributed shared memory
       cudaLaunchConfig_t lc = {};
       lc.gridDim = dim3((unsigned)(nf * frame_cs));

@@ -36,13 +36,13 @@ ENV_OPTIONS = {"LV_VOX_MAP_MB": ("vox_dense_map_limit_bytes", 1 << 20), "LV_BEV_
                "LV_DISABLE_TMA": ("disable_tma", 1), "LV_BEV_FIF": ("bev_frames_in_flight", 1),
                "LV_CANVAS_VARIANT": ("canvas_variant", 1),
                "LV_VOX_FRAME_KERNEL": ("vox_frame_kernel", 1), "LV_VOX_LIST_PATH": ("vox_list_path", 1),
-               "LV_VOX_ROWS_WAVES": ("vox_rows_waves", 1)}
+               "LV_VOX_ROWS_WAVES": ("vox_rows_waves", 1), "LV_VOX_FUSED": ("vox_fused_prologue", 1)}
 
 
 def apply_env_options(handle):
     import os
     for env, (name, scale) in ENV_OPTIONS.items():
-        if os.environ.get(env):
+        if os.environ.get(env) not in (None, ""):
             handle.set_option(name, int(os.environ[env]) * scale)
 
 
