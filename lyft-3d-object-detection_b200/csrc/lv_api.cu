@@ -161,6 +161,10 @@ int lv_set_option(lv_handle* h, const char* name, int64_t value) {
     h->bev_tma = value;
     return LV_OK;
   }
+  if (strcmp(name, "bev_fused_zero") == 0) {
+    h->bev_fused_zero = value;
+    return LV_OK;
+  }
   if (strcmp(name, "disable_tma") == 0) {
     h->disable_tma = value;
     return LV_OK;

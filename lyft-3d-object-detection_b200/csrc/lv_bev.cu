@@ -9,8 +9,9 @@
 //   points   : (N_total, stride) float32, frames/sweeps ("segments") back to back
 //   counts   : workspace u32 [frames_in_flight][S0*S1*S2], indexed (c1*S1 + c0)*S2 + c2,
 //              all-zero between calls (the finalize kernel re-zeroes what it reads);
-//              sized to stay resident in the 126 MB L2 so that the atomics and the
-//              finalize read never reach HBM.
+//              up to 192 MB in flight (128 frames of 336x336x3: 173 MB, more than the 126 MB L2 -
+//              fewer, larger launches measured faster than L2 residency, see lv_bev_rasterize); only
+//              the touched sectors ever move, tracked by a dirty bitmap (1 bit per 4 counts).
 //   outputs  : per frame (S0,S1,S2) f32 raw / f32 normalised / u8, (S2+3,S0,S1) f32 CHW
 //
 // Kernels
@@ -39,6 +40,13 @@ struct BevParams {
   unsigned* counts;
   unsigned* dirty;             // 1 bit per 4 consecutive counts ("quad"): set by the first hit of a cell
   int use_tma;                 // point rows 16-byte aligned: full tiles are staged by TMA bulk copies
+  // zero fill of the dense outputs of the sub-batch (pass A of the finalize), spread over the tiles of this kernel:
+  // it depends on nothing, and the histogram leaves the store path idle (28 % of the DRAM peak, waiting for ATOMs)
+  float4* z_raw;               // or null
+  float4* z_norm;              // or null
+  uchar4* z_u8;                // or null
+  int64_t z_quads;             // quads (4 cells) to clear
+  int z_per_tile;              // quads cleared per tile of points (ceil); 0 = the finalize kernel streams the zeros itself
 };
 
 __device__ __forceinline__ int bev_find_segment(const int64_t* __restrict__ offs, int lo, int hi, int64_t i) {
@@ -76,7 +84,7 @@ __device__ __forceinline__ int bev_find_segment_warp(const int64_t* __restrict__
 // flight while the current one is processed) and read back with conflict-free LDS (a row stride of 5 words
 // is coprime with the 32 banks).  STRIDE 0: any row stride, direct global loads.
 template <int STRIDE>
-__global__ void __launch_bounds__(BEV_THREADS) bev_hist_kernel(BevParams p) {
+__global__ void __launch_bounds__(BEV_THREADS, 4) bev_hist_kernel(BevParams p) {
   extern __shared__ __align__(128) float tiles[];  // [BEV_STAGES][BEV_TILE * STRIDE]
   __shared__ __align__(8) uint64_t bar[BEV_STAGES];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -120,6 +128,17 @@ __global__ void __launch_bounds__(BEV_THREADS) bev_hist_kernel(BevParams p) {
     // stage (k-1) % STAGES was released by the barrier that ended the previous iteration
     if (threadIdx.x == 0 && staged(t + (BEV_STAGES - 1) * t_step))
       issue(t + (BEV_STAGES - 1) * t_step, (k + BEV_STAGES - 1) % BEV_STAGES);
+    // this tile's share of the zero fill: stores that wait for nothing, issued before anything is waited for
+    if (p.z_per_tile) {
+      const int64_t q_lo = (t - t_lo) * p.z_per_tile;
+      const int n = (int)(p.z_quads - q_lo < p.z_per_tile ? p.z_quads - q_lo : p.z_per_tile);
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = threadIdx.x; q < n; q += BEV_THREADS) {
+        if (p.z_raw) lv_st_stream_f4(p.z_raw + q_lo + q, z4);
+        if (p.z_norm) lv_st_stream_f4(p.z_norm + q_lo + q, z4);
+        if (p.z_u8) p.z_u8[q_lo + q] = make_uchar4(0, 0, 0, 0);
+      }
+    }
     // segments of the warp's span (uniform across the warp), looked up while the copy is in flight
     const int64_t span0 = t * BEV_TILE + warp * BEV_WTILE;
     const int64_t v0 = span0 < p.pt_begin ? p.pt_begin : span0;
@@ -222,6 +241,7 @@ struct BevOut {
   int S0, S1, S2;
   int n_frames;        // frames in this sub-batch
   int64_t frame_base;  // first frame (output offset)
+  int zeros_done;      // the histogram kernel has already streamed the zeros of the dense outputs (pass A)
 };
 
 __device__ __forceinline__ void bev_cell(unsigned c, float max_intensity, float& raw, float& nrm, uint8_t& q) {
@@ -258,14 +278,16 @@ __global__ void __launch_bounds__(256) bev_finalize_flat4_kernel(unsigned* count
       word = o.dirty[w];
       if (word) o.dirty[w] = 0;   // the warp owns these 32 words
     }
-    // pass A
+    // pass A (unless bev_hist_kernel did it beside its atomics)
+    if (!o.zeros_done) {
 #pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-      const int64_t q = q0 + k * 32 + lane;
-      if (q < total_quads) {
-        if (raw) lv_st_stream_f4(raw + q, z4);
-        if (nrm) lv_st_stream_f4(nrm + q, z4);
-        if (u8) u8[q] = zb;
+      for (int k = 0; k < 32; ++k) {
+        const int64_t q = q0 + k * 32 + lane;
+        if (q < total_quads) {
+          if (raw) lv_st_stream_f4(raw + q, z4);
+          if (nrm) lv_st_stream_f4(nrm + q, z4);
+          if (u8) u8[q] = zb;
+        }
       }
     }
     if (!__any_sync(0xffffffffu, word != 0)) continue;
@@ -516,6 +538,22 @@ extern "C" int lv_bev_rasterize(lv_handle* h, const float* d_points, int32_t poi
     const int s1 = seg;
     p.seg_lo = s0; p.seg_hi = s1;
     p.frame_base = (int)f0;
+    o.zeros_done = 0;
+    p.z_quads = 0;
+    p.z_per_tile = 0;
+    p.z_raw = nullptr; p.z_norm = nullptr; p.z_u8 = nullptr;
+    if (!d_chw && cells % 4 == 0 && h->bev_fused_zero && s1 > s0 && h_seg_offsets[s1] > h_seg_offsets[s0] &&
+        ((reinterpret_cast<uintptr_t>(d_raw) | reinterpret_cast<uintptr_t>(d_norm)) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(d_u8) & 3) == 0) {
+      const int64_t q0 = f0 * (int64_t)(cells / 4);
+      p.z_quads = (f1 - f0) * (int64_t)(cells / 4);
+      p.z_raw = d_raw ? reinterpret_cast<float4*>(d_raw) + q0 : nullptr;
+      p.z_norm = d_norm ? reinterpret_cast<float4*>(d_norm) + q0 : nullptr;
+      p.z_u8 = d_u8 ? reinterpret_cast<uchar4*>(d_u8) + q0 : nullptr;
+      const int64_t n_tiles = lv_div_up(h_seg_offsets[s1], BEV_TILE) - h_seg_offsets[s0] / BEV_TILE;
+      p.z_per_tile = (int)lv_div_up(p.z_quads, n_tiles);
+      o.zeros_done = 1;
+    }
     if (s1 > s0) {
       p.pt_begin = h_seg_offsets[s0];
       p.pt_end = h_seg_offsets[s1];

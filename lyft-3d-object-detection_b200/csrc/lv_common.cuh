@@ -75,6 +75,10 @@ struct lv_handle {
                                       // 0.203 vs 0.158 ms stride 5, 128 frames) - the kernel is bound by the
                                       // L2 atomics, not by the loads
 
+  int64_t bev_fused_zero = 0;         // 1: bev_hist_kernel streams the zeros of the dense outputs beside its atomics (pass A of the
+                                      // finalize).  Off by default: BEV stage 0.127 vs 0.129 ms, but the pipelined step gets SLOWER
+                                      // (1.655 vs 1.640 ms) - the histogram slows by what the finalize saves and overlaps its
+                                      // neighbours worse
   int64_t vox_frame_kernel = 0;       // 1: small grids run K1-K5 in one cluster per frame (vx_frame_kernel, distributed shared
                                       // memory map).  Off by default: measured slower than the five kernels (0.71 vs 0.67 ms per
                                       // 128 pillar frames) - scattered 4-byte DSMEM accesses run at ~0.5 per cycle and SM
