@@ -195,6 +195,26 @@ def time_other_configs(dev, peak, reps=10):
         ms = timed(lambda: vg.voxelize_frames(cloud, offs, vs, rg, T, V, zero_tail=False))
         out[name] = dict({"points": n, "voxels": v_act, "ms": round(ms, 4), "points_per_s": round(n / (ms * 1e-3))},
                          **roof(16 * n + v_act * (T * 4 * 4 + 16), ms))
+    # C2 batched: six 1.06 M-point clouds per call (copies of the cloud turned about z by k x 60 degrees).  The dense
+    # first[] map of this grid is 216 MB per cloud; the open-addressing table is 16 MB, so six clouds share a launch
+    nb = 6
+    parts = [cloud]
+    for k in range(1, nb):
+        a = 2.0 * np.pi * k / nb
+        rot = torch.tensor([[np.cos(a), np.sin(a)], [-np.sin(a), np.cos(a)]], dtype=torch.float32, device=dev)
+        q = cloud.clone()
+        q[:, :2] = cloud[:, :2] @ rot
+        parts.append(q)
+    batch = torch.cat(parts).contiguous()
+    boffs = np.arange(nb + 1, dtype=np.int64) * n
+    vs, rg, T, V = synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, 60000
+    vn = vg.voxelize_frames(batch, boffs, vs, rg, T, V, zero_tail=False)[3]
+    v_tot = int(vn.sum().item())
+    ms = timed(lambda: vg.voxelize_frames(batch, boffs, vs, rg, T, V, zero_tail=False))
+    out["C2 batched: %d clouds of 1.06 M points per call" % nb] = dict(
+        {"points": nb * n, "voxels": v_tot, "ms": round(ms, 4), "ms_per_cloud": round(ms / nb, 4),
+         "points_per_s": round(nb * n / (ms * 1e-3))}, **roof(16 * nb * n + v_tot * (T * 4 * 4 + 16), ms))
+    del batch, parts
     # C4: 1024^2 x 3 BEV of the same cloud, 20 sweeps each with its own sensor->car 4x4, u8 + CHW/map
     per = n // 20
     seg_offs = np.arange(21, dtype=np.int64) * per

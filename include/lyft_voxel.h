@@ -380,6 +380,31 @@ int lv_pillar_pfn(lv_handle* h, const float* d_voxels, const int32_t* d_num_poin
                   int32_t with_distance, const float* d_weight, const float* d_scale,
                   const float* d_shift, int32_t units, float* d_out, lv_stream stream);
 
+/* PFNLayer in TRAINING form (second/second/pytorch/models/pointpillars.py:51-65 with BatchNorm1d batch
+ * statistics, and its backward) behind the fused decoration, in two device passes that never write the
+ * (P,T,C_out) decorated tensor or the (P,T,units) activations:
+ *   lv_pillar_pfn_moments   d_moments (float64, zeroed by the call) = [S1 (C_out) | upper triangle of
+ *                           M = sum f f^T row by row (C_out (C_out+1)/2)], sums over the live slots of the
+ *                           decorated features f.  The Linear has no bias and padded slots are zero, so the
+ *                           batch mean / variance of y = W f over all N = P*T slots are W S1 / N and
+ *                           diag(W M W^T) / N - mean^2; the caller turns them into the scale / shift of
+ *                           lv_pillar_pfn (the forward pass proper).
+ *   lv_pillar_pfn_backward  d_acc (float64 (units, 2 + C_out), zeroed by the call) = per channel
+ *                           [dbeta = sum g | dgamma = sum g * yhat | A = sum g * f at the slot that won the
+ *                           max], over the (pillar, channel) pairs with a positive maximum; g = d_grad_out
+ *                           (P, units).  d_mean / d_invstd are the batch statistics of the forward.
+ * Same restrictions as lv_pillar_pfn (4 features per point, max_points <= 64, units in {32, 64, 128}). */
+int lv_pillar_pfn_moments(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,
+                          const int32_t* d_coors, int64_t n_pillars, int32_t max_points, int32_t num_features,
+                          float vx, float vy, float x_offset, float y_offset, int32_t variant,
+                          int32_t with_distance, double* d_moments, lv_stream stream);
+int lv_pillar_pfn_backward(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,
+                           const int32_t* d_coors, int64_t n_pillars, int32_t max_points, int32_t num_features,
+                           float vx, float vy, float x_offset, float y_offset, int32_t variant,
+                           int32_t with_distance, const float* d_weight, const float* d_scale,
+                           const float* d_shift, const float* d_mean, const float* d_invstd, int32_t units,
+                           const float* d_grad_out, double* d_acc, lv_stream stream);
+
 /* lv_voxelize_concat + lv_pillar_pfn in one call: points in, (capacity_rows, units) pillar
  * features out (units == 64), ready for lv_pillar_scatter.  Replaces preprocess.py:299-317 +
  * :21-55, pointpillars.py:203-231 and :51-65 without writing voxels or decorated points. */

@@ -111,6 +111,10 @@ SIGNATURES = {
     "lv_pillarize_pfn_concat": (ctypes.c_int, [_vp, ctypes.POINTER(VoxelConfig), _vp, _i32, _vp, _i64, _f32, _f32,
                                                _f32, _f32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
                                                _vp, _vp]),
+    "lv_pillar_pfn_moments": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _i32, _i32,
+                                             _vp, _vp]),
+    "lv_pillar_pfn_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _i32, _i32,
+                                              _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "lv_pillar_scatter": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lv_pillar_scatter_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lv_pillar_decorate_half": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _i32, _i32,

@@ -161,6 +161,10 @@ int lv_set_option(lv_handle* h, const char* name, int64_t value) {
     h->bev_tma = value;
     return LV_OK;
   }
+  if (strcmp(name, "bev_u16") == 0) {
+    h->bev_u16 = value;
+    return LV_OK;
+  }
   if (strcmp(name, "bev_fused_zero") == 0) {
     h->bev_fused_zero = value;
     return LV_OK;
@@ -179,6 +183,10 @@ int lv_set_option(lv_handle* h, const char* name, int64_t value) {
   }
   if (strcmp(name, "vox_fused_prologue") == 0) {
     h->vox_fused_prologue = value;
+    return LV_OK;
+  }
+  if (strcmp(name, "vox_hash_map") == 0) {
+    h->vox_hash_map = value;
     return LV_OK;
   }
   if (strcmp(name, "vox_rows_waves") == 0) {

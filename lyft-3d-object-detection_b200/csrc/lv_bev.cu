@@ -22,6 +22,7 @@
 //                        requested output and clears the counts.
 //                        Algorithmic bytes: 4 (raw) [+4 norm] [+1 u8] [+ (S2+3)*4/S2 chw + 1 map] per cell.
 #include <algorithm>
+#include <vector>
 
 #include "lv_common.cuh"
 
@@ -38,6 +39,9 @@ struct BevParams {
   int S0, S1, S2;
   unsigned cells;
   unsigned* counts;
+  int u16;                     // counts are 16-bit, two per word (every frame of the call has < 65,536 points, so a
+                               // half can never carry into its neighbour): half the footprint - 128 frames of 336x336x3
+                               // are 87 MB instead of 173 MB and stay in the 126 MB L2
   unsigned* dirty;             // 1 bit per 4 consecutive counts ("quad"): set by the first hit of a cell
   int use_tma;                 // point rows 16-byte aligned: full tiles are staged by TMA bulk copies
   // zero fill of the dense outputs of the sub-batch (pass A of the finalize), spread over the tiles of this kernel:
@@ -216,7 +220,12 @@ __global__ void __launch_bounds__(BEV_THREADS, 4) bev_hist_kernel(BevParams p) {
       pend_key[r] = 0xffffffffu;
       pend_old[r] = 1;
       if (key != 0xffffffffu && lane == (__ffs(peers) - 1)) {
-        pend_old[r] = atomicAdd(p.counts + key, (unsigned)__popc(peers));
+        if (p.u16) {
+          const unsigned sh = (key & 1u) << 4;
+          pend_old[r] = (atomicAdd(p.counts + (key >> 1), (unsigned)__popc(peers) << sh) >> sh) & 0xffffu;
+        } else {
+          pend_old[r] = atomicAdd(p.counts + key, (unsigned)__popc(peers));
+        }
         pend_key[r] = key;
       }
     }
@@ -242,7 +251,24 @@ struct BevOut {
   int n_frames;        // frames in this sub-batch
   int64_t frame_base;  // first frame (output offset)
   int zeros_done;      // the histogram kernel has already streamed the zeros of the dense outputs (pass A)
+  int u16;             // 16-bit counts, two per word (see BevParams)
 };
+
+// the four counts of quad q, cleared behind the read
+__device__ __forceinline__ uint4 bev_take_quad(unsigned* counts, int64_t q, int u16) {
+  uint4 c;
+  if (u16) {
+    uint2* p2 = reinterpret_cast<uint2*>(counts) + q;
+    const uint2 w = *p2;
+    *p2 = make_uint2(0u, 0u);
+    c = make_uint4(w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16);
+  } else {
+    uint4* p4 = reinterpret_cast<uint4*>(counts) + q;
+    c = *p4;
+    *p4 = make_uint4(0u, 0u, 0u, 0u);
+  }
+  return c;
+}
 
 __device__ __forceinline__ void bev_cell(unsigned c, float max_intensity, float& raw, float& nrm, uint8_t& q) {
   raw = (float)c;                                                  // exact below 2^24
@@ -264,7 +290,6 @@ __global__ void __launch_bounds__(256) bev_finalize_flat4_kernel(unsigned* count
   const int64_t total_quads = (int64_t)(o.cells / 4) * o.n_frames;
   const int64_t n_tasks = (total_quads + 1023) >> 10;
   const int64_t out0 = (int64_t)o.frame_base * (o.cells / 4);
-  uint4* cp = reinterpret_cast<uint4*>(counts);
   float4* raw = o.raw ? reinterpret_cast<float4*>(o.raw) + out0 : nullptr;
   float4* nrm = o.norm ? reinterpret_cast<float4*>(o.norm) + out0 : nullptr;
   uchar4* u8 = o.u8 ? reinterpret_cast<uchar4*>(o.u8) + out0 : nullptr;
@@ -305,13 +330,12 @@ __global__ void __launch_bounds__(256) bev_finalize_flat4_kernel(unsigned* count
         if (col) {
           q[j] = q0 + (__ffs(col) - 1) * 32 + lane;
           col &= col - 1;
-          c[j] = cp[q[j]];
+          c[j] = bev_take_quad(counts, q[j], o.u16);
         }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (q[j] < 0) continue;
-        cp[q[j]] = make_uint4(0, 0, 0, 0);
         float4 r, n;
         uchar4 b;
         bev_cell(c[j].x, o.max_intensity, r.x, n.x, b.x);
@@ -333,8 +357,14 @@ __global__ void __launch_bounds__(256) bev_finalize_scalar_kernel(unsigned* coun
        q += (int64_t)gridDim.x * blockDim.x) {
     unsigned c = 0;
     if (o.dirty[q >> 7] & (1u << ((q >> 2) & 31))) {
-      c = counts[q];
-      counts[q] = 0;
+      if (o.u16) {
+        unsigned short* c16 = reinterpret_cast<unsigned short*>(counts);
+        c = c16[q];
+        c16[q] = 0;
+      } else {
+        c = counts[q];
+        counts[q] = 0;
+      }
     }
     const int64_t out_q = o.frame_base * (int64_t)o.cells + q;
     float r, n;
@@ -355,8 +385,7 @@ __global__ void __launch_bounds__(256) bev_finalize_hwc3_kernel(unsigned* counts
        g += (int64_t)gridDim.x * blockDim.x) {
     const int64_t f = g / groups_per_frame;
     const int64_t gi = g - f * groups_per_frame;        // (y, x/4) flattened: y*(S1/4) + x4
-    uint4* cp = reinterpret_cast<uint4*>(counts) + g * 3;  // 12 consecutive counts = 3 quads
-    unsigned c[12];
+    unsigned c[12];                                        // 12 consecutive counts = 3 quads
     bool dirty[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {   // the three bitmap loads, then the three count loads, are independent
@@ -364,12 +393,12 @@ __global__ void __launch_bounds__(256) bev_finalize_hwc3_kernel(unsigned* counts
       dirty[k] = (o.dirty[gq >> 5] >> (gq & 31)) & 1u;
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) *reinterpret_cast<uint4*>(c + 4 * k) = dirty[k] ? cp[k] : make_uint4(0, 0, 0, 0);
+    for (int k = 0; k < 3; ++k)
+      *reinterpret_cast<uint4*>(c + 4 * k) = dirty[k] ? bev_take_quad(counts, g * 3 + k, o.u16) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       if (!dirty[k]) continue;
       const unsigned gq = (unsigned)(g * 3 + k);
-      cp[k] = make_uint4(0, 0, 0, 0);
       atomicAnd(o.dirty + (gq >> 5), ~(1u << (gq & 31)));   // this thread owns the quad's bit
     }
     float r[12], n[12];
@@ -486,6 +515,16 @@ extern "C" int lv_bev_rasterize(lv_handle* h, const float* d_points, int32_t poi
   if (fif > n_frames) fif = n_frames;
   fif = lv_div_up(n_frames, lv_div_up(n_frames, fif));
   while (fif > 1 && fif * cells64 >= 0xffffffffll) --fif;
+  // 16-bit counts when no frame can overflow one (a frame's count is at most its number of points)
+  bool u16 = h->bev_u16 != 0 && cells % 4 == 0;
+  {
+    std::vector<int64_t> per_frame((size_t)n_frames, 0);
+    for (int s = 0; s < n_segments && u16; ++s) {
+      const int f = h_seg_frame ? h_seg_frame[s] : s;
+      per_frame[f] += h_seg_offsets[s + 1] - h_seg_offsets[s];
+      if (per_frame[f] > 65535) u16 = false;
+    }
+  }
   LV_CHECK(h->bev_counts.ensure((size_t)fif * cells * sizeof(unsigned), stream, 0));
   const size_t dirty_bytes = (size_t)(lv_div_up(fif * cells64, 128) + 32) * sizeof(unsigned);
   LV_CHECK(h->bev_dirty.ensure(dirty_bytes, stream, 0));
@@ -514,6 +553,7 @@ extern "C" int lv_bev_rasterize(lv_handle* h, const float* d_points, int32_t poi
   p.S0 = shape[0]; p.S1 = shape[1]; p.S2 = shape[2];
   p.cells = cells;
   p.counts = h->bev_counts.as<unsigned>();
+  p.u16 = u16 ? 1 : 0;
   p.dirty = h->bev_dirty.as<unsigned>();
   // TMA bulk copies need 16-byte aligned tiles: tile t starts at byte t * 1024 * stride * 4
   p.use_tma = (point_stride == 4 || point_stride == 5) && (reinterpret_cast<uintptr_t>(d_points) & 15) == 0 &&
@@ -528,6 +568,7 @@ extern "C" int lv_bev_rasterize(lv_handle* h, const float* d_points, int32_t poi
   o.raw = d_raw; o.norm = d_norm; o.u8 = d_u8; o.map = d_map_u8; o.chw = d_chw;
   o.max_intensity = max_intensity;
   o.cells = cells; o.S0 = shape[0]; o.S1 = shape[1]; o.S2 = shape[2];
+  o.u16 = p.u16;
 
   int seg = 0;
   for (int64_t f0 = 0; f0 < n_frames; f0 += fif) {

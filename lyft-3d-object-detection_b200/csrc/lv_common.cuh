@@ -75,6 +75,7 @@ struct lv_handle {
                                       // 0.203 vs 0.158 ms stride 5, 128 frames) - the kernel is bound by the
                                       // L2 atomics, not by the loads
 
+  int64_t bev_u16 = 1;                // 1: 16-bit BEV counts (two per word) whenever every frame of the call has < 65,536 points; 0: always 32-bit
   int64_t bev_fused_zero = 0;         // 1: bev_hist_kernel streams the zeros of the dense outputs beside its atomics (pass A of the
                                       // finalize).  Off by default: BEV stage 0.127 vs 0.129 ms, but the pipelined step gets SLOWER
                                       // (1.655 vs 1.640 ms) - the histogram slows by what the finalize saves and overlaps its
@@ -87,6 +88,8 @@ struct lv_handle {
   int64_t vox_fused_prologue = 0;     // 1: frames of <= 64 chunks run K1-K5 as ONE kernel (vx_fused_kernel: per-frame arrival counters,
                                       // look-back and polling instead of kernel boundaries).  Off by default: bit-identical, but measured
                                       // slower (0.724 vs 0.671 ms per 128 pillar frames; see the kernel's header in lv_voxel.cu)
+  int64_t vox_hash_map = 0;           // first[] as an open-addressing table sized by the points instead of a dense map sized by the
+                                      // grid: 0 = automatic (grids whose dense map exceeds 48 MB per frame), 1 = always, -1 = never
   int64_t vox_rows_waves = 0;         // CTAs of vl_rows_kernel per resident slot (0 = 4)
   int64_t canvas_variant = 0;         // 0 = auto (pillar_canvas_q_kernel when the shape allows), 1 = pillar_canvas_kernel (A/B)
 

@@ -72,7 +72,9 @@ struct VoxParams {
   unsigned row_div_m;          // ceil(2^32 / T): voxel of a flat slot index < 2^20
   unsigned div_m[2];           // exact division of a cell id (< 2^28) by gx*gy [0] and by gx [1]:
   int div_s[2];                //   q = (n * m) >> s   (vx_make_div)
-  int64_t G;                   // cells per frame
+  int64_t G;                   // int32 words of first[] per frame: cells (dense map) or 2 x slots (hash table)
+  int hash_bits;               // 0: dense map indexed by cell id.  b: open-addressing table of 2^b (key, value) slots per frame
+  int map_shift;               // 0 dense, 1 hash: entry e has its value word at e << map_shift (its key word behind it)
   int T, V, overflow, zero_tail;
   unsigned tma_bytes;          // bytes of one full chunk of rows when K1 stages them by TMA, else 0
   int low_bits, n_bins;        // bin = vid >> low_bits
@@ -133,7 +135,32 @@ __device__ __forceinline__ ChunkLoc vx_locate(const VoxParams& p) {
 // ---------------------------------------------------------------- K1: cells + first index
 // A full chunk (2048 rows) whose first row is 16-byte aligned is staged in shared memory by
 // one TMA bulk copy (cp.async.bulk + mbarrier); partial or unaligned chunks use plain loads.
-template <bool C4>
+// Open-addressing table for grids whose dense map would not stay in L2 (1056 x 1280 x 40 cells = 216 MB per cloud
+// for the 0.05 m SECOND config): 2^b slots of (value word, key word) per frame, a slot is claimed by a 64-bit CAS
+// of (cell id << 32 | point index) and lowered by a 64-bit atomicMin - the high word is equal, so the minimum is
+// the lowest point index.  Empty = every byte 0x7f, like the dense map.  Linear probing; the host sizes the table
+// at >= 1.25 x the points of the largest frame.  Returns the slot, which replaces the cell id in cell[].
+#define VX_EMPTY64 0x7f7f7f7f7f7f7f7full
+__device__ __forceinline__ int vx_hash_insert(int32_t* tab, int bits, int cell, int li) {
+  unsigned long long* t = reinterpret_cast<unsigned long long*>(tab);
+  const unsigned mask = (1u << bits) - 1u;
+  unsigned h = ((unsigned)cell * 2654435761u) >> (32 - bits);
+  const unsigned long long mine = ((unsigned long long)(unsigned)cell << 32) | (unsigned)li;
+  while (true) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(t + h);
+    if (cur == VX_EMPTY64) {
+      cur = atomicCAS(t + h, VX_EMPTY64, mine);
+      if (cur == VX_EMPTY64) return (int)h;
+    }
+    if ((unsigned)(cur >> 32) == (unsigned)cell) {
+      atomicMin(t + h, mine);
+      return (int)h;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+template <bool C4, bool HASH>
 __global__ void __launch_bounds__(VX_THREADS) vx_cells_kernel(VoxParams p) {
   extern __shared__ __align__(128) float tile[];  // [VX_CHUNK][C] when p.tma_bytes != 0
   __shared__ __align__(8) uint64_t bar;
@@ -184,11 +211,19 @@ __global__ void __launch_bounds__(VX_THREADS) vx_cells_kernel(VoxParams p) {
       if (cx >= 0.f && cx < (float)p.grid[0] && cy >= 0.f && cy < (float)p.grid[1] && cz >= 0.f &&
           cz < (float)p.grid[2])
         cell = ((int)cz * p.grid[1] + (int)cy) * p.grid[0] + (int)cx;
-      p.cell[gi - p.pt_lo] = cell;
+      if (!HASH) p.cell[gi - p.pt_lo] = cell;
     }
     // lanes of one cell: only the lowest lane (= lowest index) needs to bid
     const unsigned peers = __match_any_sync(0xffffffffu, cell);
-    if (cell >= 0 && lane == __ffs(peers) - 1) atomicMin(map + cell, li);
+    const int leader = __ffs(peers) - 1;
+    if (HASH) {
+      int slot = -1;
+      if (cell >= 0 && lane == leader) slot = vx_hash_insert(map, p.hash_bits, cell, li);
+      slot = __shfl_sync(0xffffffffu, slot, leader);
+      if (li < L.n) p.cell[L.start + li - p.pt_lo] = cell >= 0 ? slot : -1;
+    } else if (cell >= 0 && lane == leader) {
+      atomicMin(map + cell, li);
+    }
   }
 }
 
@@ -224,7 +259,7 @@ __global__ void __launch_bounds__(VX_THREADS) vx_assign_kernel(VoxParams p) {
   }
   int first[VX_ITEMS];
 #pragma unroll
-  for (int k = 0; k < VX_ITEMS; ++k) first[k] = cell[k] >= 0 ? map[cell[k]] : -1;
+  for (int k = 0; k < VX_ITEMS; ++k) first[k] = cell[k] >= 0 ? map[(int64_t)cell[k] << p.map_shift] : -1;
 #pragma unroll
   for (int k = 0; k < VX_ITEMS; ++k) {
     if (cell[k] >= 0 && first[k] == base + k) {
@@ -291,9 +326,9 @@ __global__ void __launch_bounds__(VX_THREADS) vx_assign_kernel(VoxParams p) {
     if (!(flags & (1u << k))) continue;
     const int li = base + k;
     const int c = cell[k];
-    map[c] = ~rank;  // voxel id, stored negative so it never equals a point index
+    map[(int64_t)c << p.map_shift] = ~rank;  // voxel id, stored negative so it never equals a point index
     p.cell[L.start + li - p.pt_lo] = c | VX_CREATOR_BIT;
-    ccell[rank] = c;  // rank < number of points of the frame
+    ccell[rank] = p.map_shift ? map[((int64_t)c << 1) + 1] : c;  // the voxel's cell id (hash: the slot's key word); rank < points of the frame
     if (rank == p.V && p.overflow == LV_OVERFLOW_BREAK) p.frame_cut[L.fl] = li;  // simplevis.py:48-49
     ++rank;
   }
@@ -318,7 +353,7 @@ __global__ void __launch_bounds__(VX_THREADS) vx_keys_kernel(VoxParams p) {
     craw[k] = li < L.n ? p.cell[L.start + li - p.pt_lo] : -1;
   }
 #pragma unroll
-  for (int k = 0; k < VX_ITEMS; ++k) vid[k] = craw[k] >= 0 ? ~map[craw[k] & ~VX_CREATOR_BIT] : 0x7fffffff;
+  for (int k = 0; k < VX_ITEMS; ++k) vid[k] = craw[k] >= 0 ? ~map[(int64_t)(craw[k] & ~VX_CREATOR_BIT) << p.map_shift] : 0x7fffffff;
 #pragma unroll
   for (int k = 0; k < VX_ITEMS; ++k) {
     const int li = base + k * VX_THREADS + threadIdx.x;
@@ -428,7 +463,11 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p) {
     }
 #pragma unroll
     for (int r = 0; r < VX_ITEMS; ++r)
-      if (craw[r] >= 0 && (craw[r] & VX_CREATOR_BIT)) map[craw[r] & ~VX_CREATOR_BIT] = VX_EMPTY;
+      if (craw[r] >= 0 && (craw[r] & VX_CREATOR_BIT)) {
+        const int64_t e = (int64_t)(craw[r] & ~VX_CREATOR_BIT) << p.map_shift;
+        map[e] = VX_EMPTY;
+        if (p.map_shift) map[e + 1] = VX_EMPTY;
+      }
   }
 #pragma unroll
   for (int r = 0; r < VX_ITEMS; ++r) {
@@ -1462,8 +1501,9 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   int32_t grid[3];
   LV_CHECK(lv_voxel_grid_size(cfg, grid));
   LV_REQUIRE(grid[0] > 0 && grid[1] > 0 && grid[2] > 0, "lv_voxelize: empty grid %d x %d x %d", grid[0], grid[1], grid[2]);
-  const int64_t G = (int64_t)grid[0] * grid[1] * grid[2];
-  LV_REQUIRE(G < (1ll << 28), "lv_voxelize: grid of %lld cells exceeds the dense-map limit (2^28)", (long long)G);
+  const int64_t n_cells = (int64_t)grid[0] * grid[1] * grid[2];
+  LV_REQUIRE(n_cells < (1ll << 28), "lv_voxelize: grid of %lld cells exceeds the cell-id limit (2^28)", (long long)n_cells);
+  int64_t G = n_cells;   // int32 words of first[] per frame (replaced by the hash-table size below)
   LV_REQUIRE(n_frames == 0 || h_frame_offsets[0] == 0, "lv_voxelize: frame_offsets[0] must be 0");
   if (n_frames == 0) return LV_OK;
   LV_REQUIRE((d_voxels || deco || mean_channels) && d_coords && d_num_points && d_voxel_num, "lv_voxelize: null output");
@@ -1514,6 +1554,20 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   const void* d_chunk_frame = nullptr;
   LV_CHECK(h->vox_chunk_frame.sync(chunk_frame.data(), sizeof(int32_t) * chunk_frame.size(), stream, &d_chunk_frame));
 
+  // Grids whose dense map cannot stay in L2 (> 48 MB per frame; the 0.05 m SECOND grid needs 216 MB) get an
+  // open-addressing table sized by the POINTS instead: 2^b >= 1.25 x the largest frame, 8 bytes per slot - 16 MB
+  // for a 1.06 M-point cloud, so that six clouds share one launch with every atomic in L2.
+  // vox_hash_map: 0 = automatic, 1 = always, -1 = never.
+  int64_t max_frame_pts0 = 0;
+  for (int f = 0; f < n_frames; ++f)
+    if (h_frame_offsets[f + 1] - h_frame_offsets[f] > max_frame_pts0) max_frame_pts0 = h_frame_offsets[f + 1] - h_frame_offsets[f];
+  int hash_bits = 0;
+  if (h->vox_hash_map >= 0) {
+    int b = 10;
+    while ((1ll << b) < max_frame_pts0 + max_frame_pts0 / 4 + 1) ++b;
+    if (b <= 28 && (h->vox_hash_map == 1 || (n_cells * 4 > (48ll << 20) && (8ll << b) < n_cells * 4))) hash_bits = b;
+  }
+  if (hash_bits) G = 2ll << hash_bits;
   // sub-batches: bounded by the dense map budget (L2 residency) and by the point workspace,
   // then balanced so that no launch is a small remainder
   // 96 MB of the 126 MB L2 measured best (bench.py: 64 MB 0.94 ms, 96 MB 0.90 ms, 128 MB 0.88 ms per
@@ -1538,6 +1592,7 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   }
   vx_make_div((uint32_t)grid[0] * (uint32_t)grid[1], &p.div_m[0], &p.div_s[0]);
   vx_make_div((uint32_t)grid[0], &p.div_m[1], &p.div_s[1]);
+  p.hash_bits = hash_bits; p.map_shift = hash_bits ? 1 : 0;
   p.G = G; p.T = T; p.V = V; p.overflow = cfg->overflow_mode; p.zero_tail = cfg->zero_tail;
   p.low_bits = L; p.n_bins = n_bins;
   p.voxels = d_voxels; p.coords = d_coords; p.num_points = d_num_points; p.voxel_num = d_voxel_num;
@@ -1565,8 +1620,10 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   // K1 stages full chunks by TMA when a chunk of rows is a multiple of 16 bytes and fits 64 KB
   p.tma_bytes = 0;
   if (!h->disable_tma && C <= 8 && ((size_t)VX_CHUNK * C * 4) % 16 == 0) p.tma_bytes = (unsigned)(VX_CHUNK * C * 4);
-  if (c4) LV_CHECK(vx_set_smem(vx_cells_kernel<true>, p.tma_bytes));
-  else LV_CHECK(vx_set_smem(vx_cells_kernel<false>, p.tma_bytes));
+  if (c4 && hash_bits) LV_CHECK(vx_set_smem(vx_cells_kernel<true, true>, p.tma_bytes));
+  else if (c4) LV_CHECK(vx_set_smem(vx_cells_kernel<true, false>, p.tma_bytes));
+  else if (hash_bits) LV_CHECK(vx_set_smem(vx_cells_kernel<false, true>, p.tma_bytes));
+  else LV_CHECK(vx_set_smem(vx_cells_kernel<false, false>, p.tma_bytes));
   LV_CHECK(vx_set_smem(vx_keys_kernel, smem_keys));
   LV_CHECK(vx_set_smem(vx_scatter_kernel, smem_scatter));
   if (mean_channels) {
@@ -1600,7 +1657,7 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   int64_t max_frame_pts = 0;
   for (int f = 0; f < n_frames; ++f)
     if (h_frame_offsets[f + 1] - h_frame_offsets[f] > max_frame_pts) max_frame_pts = h_frame_offsets[f + 1] - h_frame_offsets[f];
-  if (h->vox_frame_kernel != 0 && n_bins <= 512) {
+  if (h->vox_frame_kernel != 0 && n_bins <= 512 && !hash_bits) {
     for (int cs = 1; cs <= VF_MAX_CS; cs *= 2) {
       const int64_t part = lv_div_up(G, cs);
       const size_t bytes = ((size_t)part + (size_t)(VF_WARPS + VF_MAX_CS + 1) * n_bins + VF_MAX_CS * VF_WARPS + 8) * 4;
@@ -1618,7 +1675,7 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   // list path (lv_voxel_list.cuh): three kernels, order rebuilt inside the warp that writes the row.  Small dense
   // maps only (8 bytes per cell), 4-float points, rows of at most 64 slots.  OPT-IN (lv_set_option "vox_list_path" 1):
   // bit-identical, but measured slower on 128 C5 frames (see the header of lv_voxel_list.cuh).
-  const bool list_path = h->vox_list_path == 1 && frame_cs == 0 && !mean_channels && c4 && T <= 64 && (deco || out4) &&
+  const bool list_path = h->vox_list_path == 1 && frame_cs == 0 && !hash_bits && !mean_channels && c4 && T <= 64 && (deco || out4) &&
                          G * 8 <= (64ll << 20) && max_frame_pts < (1ll << VL_RANK_BITS);
   size_t smem_rows = 0;
   if (list_path) {
@@ -1635,7 +1692,7 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     LV_CHECK(vx_set_smem(vl_cells_kernel<true>, p.tma_bytes));
   }
 
-  const bool fused_ok = h->vox_fused_prologue != 0 && !list_path && n_bins <= VX_FUSED_MAX_BINS;
+  const bool fused_ok = h->vox_fused_prologue != 0 && !list_path && !hash_bits && n_bins <= VX_FUSED_MAX_BINS;
   int f0 = 0;
   while (f0 < n_frames) {
     int f1 = f0 + 1;
@@ -1776,8 +1833,10 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
       LV_LAUNCH_CHECK(h);
     } else {
       if (nchunks > 0) {
-        if (c4) vx_cells_kernel<true><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
-        else vx_cells_kernel<false><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
+        if (c4 && hash_bits) vx_cells_kernel<true, true><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
+        else if (c4) vx_cells_kernel<true, false><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
+        else if (hash_bits) vx_cells_kernel<false, true><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
+        else vx_cells_kernel<false, false><<<nchunks, VX_THREADS, p.tma_bytes, stream>>>(p);
         LV_LAUNCH_CHECK(h);
         vx_assign_kernel<<<nchunks, VX_THREADS, 0, stream>>>(p);
         LV_LAUNCH_CHECK(h);

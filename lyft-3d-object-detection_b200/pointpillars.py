@@ -157,6 +157,81 @@ def pillar_pfn(features, num_voxels, coors, vx, vy, x_offset, y_offset, weight, 
     return out
 
 
+def _pfn_moments(features, num, coors, vx, vy, x_offset, y_offset, variant, with_distance, c_in):
+    """lv_pillar_pfn_moments -> (S1 (c_in), M (c_in, c_in)) float64: sums of f and f f^T over the live slots of
+    the decorated features."""
+    lib = nat.load()
+    n_tri = c_in * (c_in + 1) // 2
+    mom = torch.empty((c_in + n_tri,), dtype=torch.float64, device=features.device)
+    P, T, C = features.shape
+    h = nat.get_handle(features.device.index)
+    with torch.cuda.device(features.device):
+        nat.check(lib.lv_pillar_pfn_moments(h.ptr, features.data_ptr(), num.data_ptr(), coors.data_ptr(), P, T, C,
+                                            _f32(vx), _f32(vy), _f32(x_offset), _f32(y_offset),
+                                            nat.PILLAR_VARIANTS[variant], int(bool(with_distance)), mom.data_ptr(),
+                                            nat.current_stream_ptr(features.device)))
+    iu = torch.triu_indices(c_in, c_in, device=features.device)
+    M = torch.zeros((c_in, c_in), dtype=torch.float64, device=features.device)
+    M[iu[0], iu[1]] = mom[c_in:]
+    M = M + M.triu(1).T
+    return mom[:c_in], M
+
+
+class _FusedPfnTrain(torch.autograd.Function):
+    """relu(BatchNorm1d_train(Linear(decorate(voxels)))) max-pooled over the points of a pillar
+    (pointpillars.py:51-65 behind :203-231) as ONE differentiable op on the CUDA library: neither the
+    (P,T,C_in) decorated tensor nor the (P,T,units) activations exist in HBM, in the forward or in the
+    backward.  Returns (out (P, units), batch mean (units), biased batch variance (units))."""
+
+    @staticmethod
+    def forward(ctx, features, num, coors, weight, gamma, beta, eps, geom):
+        vx, vy, xo, yo, variant, with_distance = geom
+        units, c_in = weight.shape
+        P, T, _ = features.shape
+        N = float(P * T)
+        S1, M = _pfn_moments(features, num, coors, vx, vy, xo, yo, variant, with_distance, c_in)
+        Wd = weight.detach().double()
+        mean = (Wd @ S1) / N
+        ey2 = torch.einsum("ck,kl,cl->c", Wd, M, Wd) / N
+        var = (ey2 - mean * mean).clamp_min(0.0)
+        invstd = torch.rsqrt(var + eps)
+        scale = gamma.detach().double() * invstd
+        shift = beta.detach().double() - mean * scale
+        scale_f, shift_f = scale.float().contiguous(), shift.float().contiguous()
+        w_f = weight.detach().float().contiguous()
+        out = pillar_pfn(features, num, coors, vx, vy, xo, yo, w_f, scale_f, shift_f, variant=variant,
+                         with_distance=with_distance)
+        ctx.geom, ctx.N = geom, N
+        ctx.save_for_backward(features, num, coors, w_f, scale_f, shift_f, mean, invstd, S1, M, gamma.detach().double())
+        ctx.mark_non_differentiable(mean, var)
+        return out, mean, var
+
+    @staticmethod
+    def backward(ctx, grad_out, _gm, _gv):
+        features, num, coors, w_f, scale_f, shift_f, mean, invstd, S1, M, gamma = ctx.saved_tensors
+        vx, vy, xo, yo, variant, with_distance = ctx.geom
+        units, c_in = w_f.shape
+        P, T, C = features.shape
+        N = ctx.N
+        lib = nat.load()
+        g = grad_out.float().contiguous()
+        acc = torch.empty((units, 2 + c_in), dtype=torch.float64, device=features.device)
+        mean_f, invstd_f = mean.float().contiguous(), invstd.float().contiguous()
+        h = nat.get_handle(features.device.index)
+        with torch.cuda.device(features.device):
+            nat.check(lib.lv_pillar_pfn_backward(
+                h.ptr, features.data_ptr(), num.data_ptr(), coors.data_ptr(), P, T, C, _f32(vx), _f32(vy), _f32(xo),
+                _f32(yo), nat.PILLAR_VARIANTS[variant], int(bool(with_distance)), w_f.data_ptr(), scale_f.data_ptr(),
+                shift_f.data_ptr(), mean_f.data_ptr(), invstd_f.data_ptr(), units, g.data_ptr(), acc.data_ptr(),
+                nat.current_stream_ptr(features.device)))
+        dbeta, dgamma, A = acc[:, 0], acc[:, 1], acc[:, 2:]
+        # BatchNorm backward over all N slots, written with the moments: sum_live f = S1, sum_live yhat_c f = invstd_c (W M - mean S1)_c
+        Wd = w_f.double()
+        yhat_f = invstd[:, None] * (Wd @ M - mean[:, None] * S1[None, :])
+        dW = (gamma * invstd)[:, None] * (A - (dbeta / N)[:, None] * S1[None, :] - (dgamma / N)[:, None] * yhat_f)
+        return None, None, None, dW.float(), dgamma.float(), dbeta.float(), None, None
+
+
 class PFNLayer(nn.Module):
     """pointpillars.py:17-65 - unchanged PyTorch layer (Linear, BatchNorm1d eps=1e-3
     momentum=0.01, ReLU, max over the points of a pillar)."""
@@ -212,7 +287,7 @@ class _PillarFeatureNetBase(nn.Module):
                                 variant=self._variant, with_distance=self._with_distance)
 
     def can_fuse(self, features):
-        """The fused kernel is inference-only: eval mode, one PFNLayer, 4 input features,
+        """The fused inference kernel: eval mode, one PFNLayer, 4 input features,
         <= 64 points per pillar, 32/64/128 units, and nothing that needs a gradient."""
         if self.training or len(self.pfn_layers) != 1 or features.dtype != torch.float32:
             return False
@@ -222,7 +297,42 @@ class _PillarFeatureNetBase(nn.Module):
         needs_grad = features.requires_grad or any(q.requires_grad for q in layer.parameters())
         return not (torch.is_grad_enabled() and needs_grad)
 
+    fuse_training = True    # class-wide switch of the fused training path (set False to run the PyTorch PFNLayer)
+
+    def can_fuse_training(self, features):
+        """The fused training path: train mode, one PFNLayer with BatchNorm1d (no Linear bias), 4 input
+        features, <= 64 points per pillar, 32/64/128 units, float32 voxels that need no gradient."""
+        if not (self.training and self.fuse_training) or len(self.pfn_layers) != 1 or features.dtype != torch.float32:
+            return False
+        layer = self.pfn_layers[0]
+        if not isinstance(layer.norm, nn.BatchNorm1d) or not layer.norm.affine or layer.linear.bias is not None:
+            return False
+        if features.dim() != 3 or features.shape[2] != 4 or features.shape[1] > 64 or layer.units not in (32, 64, 128):
+            return False
+        if layer.linear.weight.dtype != torch.float32 or features.shape[0] * features.shape[1] < 2:
+            return False
+        return features.is_cuda and not features.requires_grad
+
+    def _forward_training_fused(self, features, num_voxels, coors):
+        layer = self.pfn_layers[0]
+        bn = layer.norm
+        feats = features.contiguous()
+        num = num_voxels.to(torch.int32).contiguous()
+        co = coors.to(torch.int32).contiguous()
+        geom = (self.vx, self.vy, self.x_offset, self.y_offset, self._variant, self._with_distance)
+        out, mean, var = _FusedPfnTrain.apply(feats, num, co, layer.linear.weight, bn.weight, bn.bias, bn.eps, geom)
+        if bn.track_running_stats:     # what nn.BatchNorm1d does in train mode (momentum 0.01, unbiased running_var)
+            with torch.no_grad():
+                n = float(feats.shape[0] * feats.shape[1])
+                bn.num_batches_tracked += 1
+                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1.0 - m).add_(mean.to(bn.running_mean.dtype), alpha=m)
+                bn.running_var.mul_(1.0 - m).add_((var * (n / (n - 1.0))).to(bn.running_var.dtype), alpha=m)
+        return out.squeeze()
+
     def forward(self, features, num_voxels, coors):
+        if self.can_fuse_training(features):
+            return self._forward_training_fused(features, num_voxels, coors)
         if self.can_fuse(features):
             w, scale, shift = fold_pfn_layer(self.pfn_layers[0])
             out = pillar_pfn(features, num_voxels, coors, self.vx, self.vy, self.x_offset, self.y_offset, w, scale,

@@ -202,3 +202,55 @@ def test_tma_staged_tiles_ragged_frames_and_unaligned_views(bev, bo, stride):
             for f in range(len(sizes)):
                 assert np.array_equal(got[f], refs[f]), (stride, shift, on, f)
             assert np.array_equal(res["u8"][2].cpu().numpy(), bo.quantize_u8(bo.normalize_voxel_intensities(refs[2])))
+
+
+def test_u16_counts_and_fused_zero_fill_change_nothing(bev, bo):
+    """Options of the histogram: 16-bit packed counts (the default whenever every frame of a call has fewer than
+    65,536 points; lv_set_option("bev_u16", 0) forces 32-bit) and the zero fill inside the histogram kernel
+    ("bev_fused_zero").  Every combination gives the same bytes - including a frame with 20,000 copies of one point
+    (a count far above the uint8 saturation), the 1024^2 CHW path, and a call in which one frame has 70,000 points
+    (falls back to 32-bit counts by itself)."""
+    import torch
+    from lyft3d_b200 import _native as nat
+    h = nat.get_handle(0)
+    hot = np.tile(np.array([[1.3, -2.2, -0.5, 0.5]], dtype=np.float32), (20000, 1))
+    small = [synth.c5_frame(f)[:40000] for f in range(3)] + [hot, synth.c5_frame(5)[:1]]
+    big = small + [np.concatenate([synth.c5_frame(6), synth.c5_frame(7)])[:70000]]
+    for frames in (small, big):
+        rows = torch.from_numpy(np.concatenate(frames)).cuda()
+        offs = np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]).astype(np.int64)
+        outs = []
+        for u16 in (1, 0):
+            for fz in (0, 1):
+                h.set_option("bev_u16", u16)
+                h.set_option("bev_fused_zero", fz)
+                try:
+                    for _ in range(2):      # twice: the counts and the bitmap must be left all-zero
+                        res = bev.rasterize_frames(rows, offs, synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE, synth.BEV_Z_OFFSET,
+                                                   want=("raw", "norm", "u8"))
+                finally:
+                    h.set_option("bev_u16", 1)
+                    h.set_option("bev_fused_zero", 0)
+                outs.append({k: v.clone() for k, v in res.items()})
+        for o in outs[1:]:
+            for k in ("raw", "norm", "u8"):
+                assert torch.equal(outs[0][k], o[k]), k
+        for f in (0, 3, 4, len(frames) - 1):
+            ref = bo.create_voxel_pointcloud(np.ascontiguousarray(frames[f].T), synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE,
+                                             synth.BEV_Z_OFFSET)
+            assert np.array_equal(outs[0]["raw"][f].cpu().numpy(), ref), f
+        assert float(outs[0]["raw"][3].max()) == 20000.0
+    # the CHW / map path (hwc3 finalize) in both count widths
+    maps = torch.from_numpy(synth.map_raster(seed=4000)[None]).cuda()
+    rows = torch.from_numpy(synth.c5_frame(1)).cuda()
+    offs = np.array([0, rows.shape[0]], dtype=np.int64)
+    chw = []
+    for u16 in (1, 0):
+        h.set_option("bev_u16", u16)
+        try:
+            res = bev.rasterize_frames(rows, offs, synth.BEV1024_SHAPE, synth.BEV1024_VOXEL_SIZE, synth.BEV_Z_OFFSET,
+                                       want=("u8", "chw"), map_u8=maps)
+        finally:
+            h.set_option("bev_u16", 1)
+        chw.append((res["u8"].clone(), res["chw"].clone()))
+    assert torch.equal(chw[0][0], chw[1][0]) and torch.equal(chw[0][1], chw[1][1])

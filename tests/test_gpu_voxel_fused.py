@@ -125,3 +125,40 @@ def test_fused_prologue_batch_engine_outputs_and_repetition(env):
     a, b = _both(nat, lambda: vg.voxelize_mean_frames(pts, offs, synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, 20000))
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("mode", ["continue", "break"])
+def test_hash_table_equals_dense_map_and_oracle(env, mode):
+    """first[] as an open-addressing table sized by the points (automatic for grids whose dense map exceeds 48 MB
+    per frame - the 0.05 m SECOND grid - lv_set_option("vox_hash_map", 1 / -1) forces / forbids it): bit-identical
+    to the dense map on the SECOND and the pillar grids, several clouds per launch, and equal to the oracle."""
+    torch, nat, vg, vo = env
+    h = nat.get_handle(0)
+    sizes = [200000, 53146, 1, 120001]
+    frames = _frames(sizes)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    for vs, rg, T, V in ((synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, 60000),
+                         (synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, 2500),
+                         (synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)):
+        outs = {}
+        for opt in (-1, 1, 0):
+            h.set_option("vox_hash_map", opt)
+            try:
+                outs[opt] = vg.voxelize_frames(pts, offs, vs, rg, T, V, overflow=mode, zero_tail=True)
+                again = vg.voxelize_frames(pts, offs, vs, rg, T, V, overflow=mode, zero_tail=True)   # table left empty?
+            finally:
+                h.set_option("vox_hash_map", 0)
+            for x, y in zip(outs[opt], again):
+                assert torch.equal(x, y), opt
+        for opt in (1, 0):
+            for x, y in zip(outs[-1], outs[opt]):
+                assert torch.equal(x, y), opt
+        vnum = outs[1][3].cpu().numpy()
+        for f in (0, 2, 3):
+            v, c, n = vo.points_to_voxel(frames[f], vs, rg, T, V, overflow=mode)
+            k = int(vnum[f])
+            assert k == v.shape[0]
+            assert np.array_equal(outs[1][1][f, :k].cpu().numpy(), c)
+            assert np.array_equal(outs[1][2][f, :k].cpu().numpy(), n)
+            assert np.array_equal(outs[1][0][f, :k].cpu().numpy().view(np.uint32), v.view(np.uint32))
