@@ -254,20 +254,17 @@ struct BevOut {
   int u16;             // 16-bit counts, two per word (see BevParams)
 };
 
-// the four counts of quad q, cleared behind the read
-__device__ __forceinline__ uint4 bev_take_quad(unsigned* counts, int64_t q, int u16) {
-  uint4 c;
+// the four counts of quad q / their reset (kept apart: the finalize kernels issue all their loads before the first store)
+__device__ __forceinline__ uint4 bev_load_quad(const unsigned* counts, int64_t q, int u16) {
   if (u16) {
-    uint2* p2 = reinterpret_cast<uint2*>(counts) + q;
-    const uint2 w = *p2;
-    *p2 = make_uint2(0u, 0u);
-    c = make_uint4(w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16);
-  } else {
-    uint4* p4 = reinterpret_cast<uint4*>(counts) + q;
-    c = *p4;
-    *p4 = make_uint4(0u, 0u, 0u, 0u);
+    const uint2 w = reinterpret_cast<const uint2*>(counts)[q];
+    return make_uint4(w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16);
   }
-  return c;
+  return reinterpret_cast<const uint4*>(counts)[q];
+}
+__device__ __forceinline__ void bev_clear_quad(unsigned* counts, int64_t q, int u16) {
+  if (u16) reinterpret_cast<uint2*>(counts)[q] = make_uint2(0u, 0u);
+  else reinterpret_cast<uint4*>(counts)[q] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 __device__ __forceinline__ void bev_cell(unsigned c, float max_intensity, float& raw, float& nrm, uint8_t& q) {
@@ -330,12 +327,13 @@ __global__ void __launch_bounds__(256) bev_finalize_flat4_kernel(unsigned* count
         if (col) {
           q[j] = q0 + (__ffs(col) - 1) * 32 + lane;
           col &= col - 1;
-          c[j] = bev_take_quad(counts, q[j], o.u16);
+          c[j] = bev_load_quad(counts, q[j], o.u16);
         }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (q[j] < 0) continue;
+        bev_clear_quad(counts, q[j], o.u16);
         float4 r, n;
         uchar4 b;
         bev_cell(c[j].x, o.max_intensity, r.x, n.x, b.x);
@@ -394,11 +392,12 @@ __global__ void __launch_bounds__(256) bev_finalize_hwc3_kernel(unsigned* counts
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-      *reinterpret_cast<uint4*>(c + 4 * k) = dirty[k] ? bev_take_quad(counts, g * 3 + k, o.u16) : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(c + 4 * k) = dirty[k] ? bev_load_quad(counts, g * 3 + k, o.u16) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       if (!dirty[k]) continue;
       const unsigned gq = (unsigned)(g * 3 + k);
+      bev_clear_quad(counts, g * 3 + k, o.u16);
       atomicAnd(o.dirty + (gq >> 5), ~(1u << (gq & 31)));   // this thread owns the quad's bit
     }
     float r[12], n[12];

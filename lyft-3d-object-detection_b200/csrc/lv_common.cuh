@@ -75,7 +75,10 @@ struct lv_handle {
                                       // 0.203 vs 0.158 ms stride 5, 128 frames) - the kernel is bound by the
                                       // L2 atomics, not by the loads
 
-  int64_t bev_u16 = 1;                // 1: 16-bit BEV counts (two per word) whenever every frame of the call has < 65,536 points; 0: always 32-bit
+  int64_t bev_u16 = 0;                // 1: 16-bit BEV counts, two per word, whenever every frame of the call has < 65,536 points (128 frames
+                                      // of 336x336x3: 87 MB instead of 173 MB, L2-resident).  Off by default: measured SLOWER, 0.153 vs
+                                      // 0.130 ms (histogram 73 vs 55 us: the three z-cells of an (x, y) column now share words, and
+                                      // same-word atomics serialise in L2; the finalize gains nothing, 71 vs 65 us)
   int64_t bev_fused_zero = 0;         // 1: bev_hist_kernel streams the zeros of the dense outputs beside its atomics (pass A of the
                                       // finalize).  Off by default: BEV stage 0.127 vs 0.129 ms, but the pipelined step gets SLOWER
                                       // (1.655 vs 1.640 ms) - the histogram slows by what the finalize saves and overlaps its

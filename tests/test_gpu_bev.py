@@ -205,8 +205,8 @@ def test_tma_staged_tiles_ragged_frames_and_unaligned_views(bev, bo, stride):
 
 
 def test_u16_counts_and_fused_zero_fill_change_nothing(bev, bo):
-    """Options of the histogram: 16-bit packed counts (the default whenever every frame of a call has fewer than
-    65,536 points; lv_set_option("bev_u16", 0) forces 32-bit) and the zero fill inside the histogram kernel
+    """Options of the histogram: 16-bit packed counts (lv_set_option("bev_u16", 1): used whenever every frame of a call
+    has fewer than 65,536 points; measured slower, so not the default) and the zero fill inside the histogram kernel
     ("bev_fused_zero").  Every combination gives the same bytes - including a frame with 20,000 copies of one point
     (a count far above the uint8 saturation), the 1024^2 CHW path, and a call in which one frame has 70,000 points
     (falls back to 32-bit counts by itself)."""
@@ -229,7 +229,7 @@ def test_u16_counts_and_fused_zero_fill_change_nothing(bev, bo):
                         res = bev.rasterize_frames(rows, offs, synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE, synth.BEV_Z_OFFSET,
                                                    want=("raw", "norm", "u8"))
                 finally:
-                    h.set_option("bev_u16", 1)
+                    h.set_option("bev_u16", 0)
                     h.set_option("bev_fused_zero", 0)
                 outs.append({k: v.clone() for k, v in res.items()})
         for o in outs[1:]:
@@ -251,6 +251,6 @@ def test_u16_counts_and_fused_zero_fill_change_nothing(bev, bo):
             res = bev.rasterize_frames(rows, offs, synth.BEV1024_SHAPE, synth.BEV1024_VOXEL_SIZE, synth.BEV_Z_OFFSET,
                                        want=("u8", "chw"), map_u8=maps)
         finally:
-            h.set_option("bev_u16", 1)
+            h.set_option("bev_u16", 0)
         chw.append((res["u8"].clone(), res["chw"].clone()))
     assert torch.equal(chw[0][0], chw[1][0]) and torch.equal(chw[0][1], chw[1][1])
