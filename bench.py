@@ -214,7 +214,32 @@ def time_other_configs(dev, peak, reps=10):
     out["C2 batched: %d clouds of 1.06 M points per call" % nb] = dict(
         {"points": nb * n, "voxels": v_tot, "ms": round(ms, 4), "ms_per_cloud": round(ms / nb, 4),
          "points_per_s": round(nb * n / (ms * 1e-3))}, **roof(16 * nb * n + v_tot * (T * 4 * 4 + 16), ms))
-    del batch, parts
+    # C3 batched: the same six clouds at the pillar config (dense 640 KB map per cloud): what a batch of ten-sweep
+    # samples costs per call
+    vs, rg, T, V = synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000
+    vn = vg.voxelize_frames(batch, boffs, vs, rg, T, V, zero_tail=False)[3]
+    v_tot = int(vn.sum().item())
+    ms = timed(lambda: vg.voxelize_frames(batch, boffs, vs, rg, T, V, zero_tail=False))
+    out["C3 batched: %d clouds of 1.06 M points per call" % nb] = dict(
+        {"points": nb * n, "voxels": v_tot, "ms": round(ms, 4), "ms_per_cloud": round(ms / nb, 4),
+         "points_per_s": round(nb * n / (ms * 1e-3))}, **roof(16 * nb * n + v_tot * (T * 4 * 4 + 16), ms))
+    # C4 batched: six frames of 20 sweeps each (per-sweep 4x4) -> 1024^2 x 3 u8 + CHW with the map channels
+    per = n // 20
+    seg_offs6 = np.arange(20 * nb + 1, dtype=np.int64) * per
+    seg_frame6 = np.repeat(np.arange(nb, dtype=np.int32), 20)
+    seg_tm6 = np.concatenate([np.stack([synth.sweep_transform(s) for s in range(20)])] * nb)
+    maps6 = torch.from_numpy(synth.map_raster(seed=4000)[None]).to(dev).expand(nb, -1, -1, -1).contiguous()
+    res6 = {"u8": torch.empty((nb,) + synth.BEV1024_SHAPE, dtype=torch.uint8, device=dev),
+            "chw": torch.empty((nb, 6, 1024, 1024), dtype=torch.float32, device=dev)}
+    b6 = batch[:20 * nb * per]
+    ms = timed(lambda: bev.rasterize_frames(b6, seg_offs6, synth.BEV1024_SHAPE, synth.BEV1024_VOXEL_SIZE,
+                                            synth.BEV_Z_OFFSET, seg_frame=seg_frame6, seg_tm=seg_tm6,
+                                            n_frames=nb, want=("u8", "chw"), map_u8=maps6, out=res6))
+    hw6 = 1024 * 1024
+    out["C4 batched: %d frames of 20 sweeps per call" % nb] = dict(
+        {"points": int(b6.shape[0]), "ms": round(ms, 4), "ms_per_frame": round(ms / nb, 4),
+         "points_per_s": round(b6.shape[0] / (ms * 1e-3))}, **roof(16 * b6.shape[0] + nb * (3 * hw6 + 3 * hw6 + 24 * hw6), ms))
+    del batch, parts, res6, maps6
     # C4: 1024^2 x 3 BEV of the same cloud, 20 sweeps each with its own sensor->car 4x4, u8 + CHW/map
     per = n // 20
     seg_offs = np.arange(21, dtype=np.int64) * per

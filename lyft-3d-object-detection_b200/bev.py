@@ -135,7 +135,14 @@ def rasterize_frames(points_rows, frame_offsets, shape, voxel_size, z_offset=0.0
     def alloc(key, shp_, dt):
         if key in out:
             return out[key]
-        return np.empty(shp_, dtype=dt)
+        # results land in pinned host memory (blocks of torch's caching host allocator): one DMA instead of
+        # the driver's pageable staging
+        import torch
+        n = int(np.prod(shp_))
+        if n == 0:
+            return np.empty(shp_, dtype=dt)
+        tdt = {np.float32: torch.float32, np.uint8: torch.uint8}[dt]
+        return torch.empty((n,), dtype=tdt, pin_memory=True).numpy().reshape(shp_)
     if "raw" in want:
         res["raw"] = alloc("raw", (n_frames, S0, S1, S2), np.float32)
     if "norm" in want:

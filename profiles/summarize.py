@@ -19,6 +19,15 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum",
+        # L2 atomic throughput and residency (north_star: "L2 atomic throughput"): sectors of ATOM / RED requests, how
+        # many found their line in L2, and how busy the L2 atomic units were
+        "lts__t_sectors_srcunit_tex_op_atom.sum", "lts__t_sectors_srcunit_tex_op_atom_dot_alu_lookup_hit.sum",
+        "lts__t_sectors_srcunit_tex_op_atom_dot_alu_lookup_miss.sum", "lts__t_sectors_srcunit_tex_op_atom_dot_cas.sum",
+        "lts__t_sectors_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_tex_op_red_lookup_hit.sum",
+        "lts__t_sectors_srcunit_tex_op_red_lookup_miss.sum",
+        "lts__t_sectors_srcunit_tex_op_atom.sum.pct_of_peak_sustained_elapsed",
+        "lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
         "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
         "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
