@@ -344,6 +344,36 @@ def time_reference_gpu_eager(eng, pts, reps=5):
     res["speedup_decorate"] = round(res["decorate_ms_reference_eager"] / res["decorate_ms_ours"], 2)
     res["speedup_scatter"] = round(res["scatter_ms_reference_eager"] / res["scatter_ms_ours"], 2)
     torch.cuda.empty_cache()
+    # a TRAINING step of the pillar feature net (pointpillars.py:203-231 + :51-65: decoration, Linear, BatchNorm1d with
+    # batch statistics, ReLU, max; forward + backward for linear.weight, norm.weight, norm.bias) on 16 frames of the
+    # batch: the reference's eager chain (it keeps the (P,60,9) and (P,60,64) tensors for autograd) beside the fused
+    # op (lv_pillar_pfn_moments + lv_pillar_pfn + lv_pillar_pfn_backward)
+    from lyft3d_b200 import pointpillars as pp, synth
+    nsub = int(eng.voxel_offsets[min(16, eng.F)].item())
+    vs_, ns_, cs_ = v[:nsub], num[:nsub], co[:nsub]
+    torch.manual_seed(0)
+    net = pp.PillarFeatureNet(4, True, (64,), False, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE).to(v.device).train()
+    g = torch.randn(nsub, 64, device=v.device)
+
+    def step_fused():
+        net.zero_grad(set_to_none=True)
+        (net(vs_, ns_, cs_) * g).sum().backward()
+
+    def step_eager():
+        net.zero_grad(set_to_none=True)
+        dec_ = tr.decorate(vs_, ns_, cs_, vx, vy, xo, yo)
+        (net.pfn_layers[0](dec_).squeeze() * g).sum().backward()
+    res["pfn_training_step"] = {"pillars": nsub, "frames": min(16, eng.F),
+                                "ms_ours_fused": round(timed(step_fused), 4)}
+    try:
+        res["pfn_training_step"]["ms_reference_eager"] = round(timed(step_eager, reps=3), 4)
+        res["pfn_training_step"]["speedup"] = round(res["pfn_training_step"]["ms_reference_eager"] /
+                                                    res["pfn_training_step"]["ms_ours_fused"], 2)
+    except torch.cuda.OutOfMemoryError as e:      # (P,60,64) activations and their gradients: several GB each
+        res["pfn_training_step"]["ms_reference_eager"] = None
+        res["pfn_training_step"]["note"] = "the eager chain ran out of memory: %s" % str(e)[:80]
+    del net, g
+    torch.cuda.empty_cache()
     return res
 
 
