@@ -1,6 +1,8 @@
 """GPU parity of the device PNG encoder (lv_png_encode): byte-identical to oracle/png_oracle.py and
 decode-exact under cv2 (the reference writes with cv2.imwrite, generating_train_bev.py:215,224, and reads
 with cv2.imread, dataset.py:83-90)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -110,3 +112,35 @@ def test_files_written_straight_into_mapped_host_memory(bev):
     sizes = ms.tensor.numpy()
     _check([mo.tensor[f, :sizes[f]].numpy().tobytes() for f in range(4)], img)
     assert not mo.tensor[0, sizes[0]:].any()             # nothing beyond the file is touched
+
+
+def test_write_training_pngs_equals_the_reference_loop_body(tmp_path):
+    """bev.write_training_pngs = the per-sample body of prepare_training_data_for_scene
+    (generating_train_bev.py:208-224) for a list of samples: the files it writes decode (cv2.imread, what
+    dataset.py:83-90 does) to exactly what the oracle chain from_file -> transform -> create_voxel_pointcloud ->
+    normalize -> round*255 and draw_boxes produce."""
+    import cv2
+    from lyft3d_b200 import bev
+    from oracle import bev_oracle as bo
+    from oracle import draw_oracle
+    raw5 = synth.load_fixture_raw()
+    sweeps = [raw5[: 30000 + 7000 * i] for i in range(3)] + [raw5[:0]]
+    tms = [synth.sweep_transform(3 * i + 1) for i in range(4)]
+    scenes = [synth.box_scene(7100 + i, 25 + 10 * i) for i in range(3)] + [(np.zeros((0, 3, 4)), np.zeros((0,), np.int32))]
+    corners = np.concatenate([c for c, _ in scenes])
+    colors = np.concatenate([k + 1 for _, k in scenes]).astype(np.int32)
+    box_offs = np.concatenate([[0], np.cumsum([c.shape[0] for c, _ in scenes])]).astype(np.int64)
+    tokens = ["tok%d" % i for i in range(4)]
+    paths = bev.write_training_pngs(sweeps, tms, corners, colors, box_offs, tokens, str(tmp_path), synth.BEV_SHAPE,
+                                    synth.BEV_VOXEL_SIZE, synth.BEV_Z_OFFSET)
+    assert [os.path.basename(a) for a, _ in paths] == ["tok%d_input.png" % i for i in range(4)]
+    for i, (a, b) in enumerate(paths):
+        cloud = bo.sensor_to_car(np.ascontiguousarray(sweeps[i][:, :4].T), tms[i])
+        ref = bo.quantize_u8(bo.normalize_voxel_intensities(
+            bo.create_voxel_pointcloud(cloud, synth.BEV_SHAPE, synth.BEV_VOXEL_SIZE, synth.BEV_Z_OFFSET)))
+        got = cv2.imread(a, cv2.IMREAD_UNCHANGED)
+        assert got.shape == ref.shape and np.array_equal(got, ref), i
+        tgt = np.zeros(synth.BEV_SHAPE, dtype=np.float32)
+        draw_oracle.draw_boxes(tgt, synth.BEV_VOXEL_SIZE, list(scenes[i][0]), list(scenes[i][1] + 1), synth.BEV_Z_OFFSET)
+        got_t = cv2.imread(b, cv2.IMREAD_UNCHANGED)
+        assert got_t.shape == (336, 336) and np.array_equal(got_t, tgt[:, :, 0].astype(np.uint8)), i
