@@ -185,6 +185,10 @@ int lv_set_option(lv_handle* h, const char* name, int64_t value) {
     h->vox_fused_prologue = value;
     return LV_OK;
   }
+  if (strcmp(name, "vox_generic_rows") == 0) {
+    h->vox_generic_rows = value;
+    return LV_OK;
+  }
   if (strcmp(name, "vox_hash_map") == 0) {
     h->vox_hash_map = value;
     return LV_OK;

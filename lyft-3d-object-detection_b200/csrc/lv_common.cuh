@@ -91,6 +91,7 @@ struct lv_handle {
   int64_t vox_fused_prologue = 0;     // 1: frames of <= 64 chunks run K1-K5 as ONE kernel (vx_fused_kernel: per-frame arrival counters,
                                       // look-back and polling instead of kernel boundaries).  Off by default: bit-identical, but measured
                                       // slower (0.724 vs 0.671 ms per 128 pillar frames; see the kernel's header in lv_voxel.cu)
+  int64_t vox_generic_rows = 0;       // 1: the fused decoration always runs the generic row writer (A/B against the T = 60 / 9-channel one)
   int64_t vox_hash_map = 0;           // first[] as an open-addressing table sized by the points instead of a dense map sized by the
                                       // grid: 0 = automatic (grids whose dense map exceeds 48 MB per frame), 1 = always, -1 = never
   int64_t vox_rows_waves = 0;         // CTAs of vl_rows_kernel per resident slot (0 = 4)
