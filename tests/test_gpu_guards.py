@@ -174,3 +174,50 @@ def test_block_filter_and_target_raster_stay_inside(env):
     torch.cuda.synchronize()
     assert tgt.intact()
     assert not tgt.t[0].any() and tgt.t[2].any() and int(tgt.t.max()) <= 9
+
+
+def test_pfn_training_kernels_and_hash_table_outputs(env):
+    """lv_pillar_pfn_moments / lv_pillar_pfn_backward write exactly C_out + C_out(C_out+1)/2 and units x (2 + C_out)
+    doubles; the voxelizer with the open-addressing table writes exactly the rows it was given."""
+    torch, nat, lib, h, make_cfg = env
+    dev = torch.device("cuda", 0)
+    st = nat.current_stream_ptr(dev)
+    P, T = 777, 20
+    v = torch.rand((P, T, 4), device=dev)
+    n = torch.randint(1, T + 1, (P,), device=dev, dtype=torch.int32)
+    v = v * (torch.arange(T, device=dev)[None, :, None] < n[:, None, None])
+    c = torch.zeros((P, 4), device=dev, dtype=torch.int32)
+    c[:, 2] = torch.arange(P, device=dev) % 400
+    c[:, 3] = torch.arange(P, device=dev) // 400
+    for variant, wd, cout in ((0, 0, 9), (2, 0, 8), (3, 1, 10)):
+        mom = Guarded((cout + cout * (cout + 1) // 2,), torch.float64, dev)
+        nat.check(lib.lv_pillar_pfn_moments(h.ptr, v.data_ptr(), n.data_ptr(), c.data_ptr(), P, T, 4, 0.25, 0.25, -49.875,
+                                            -49.875, variant, wd, mom.t.data_ptr(), st))
+        for units in (32, 64, 128):
+            w = torch.randn((units, cout), device=dev)
+            sc, sh, mu, isd = (torch.rand((units,), device=dev) + 0.5 for _ in range(4))
+            g = torch.randn((P, units), device=dev)
+            acc = Guarded((units, 2 + cout), torch.float64, dev)
+            nat.check(lib.lv_pillar_pfn_backward(h.ptr, v.data_ptr(), n.data_ptr(), c.data_ptr(), P, T, 4, 0.25, 0.25,
+                                                 -49.875, -49.875, variant, wd, w.data_ptr(), sc.data_ptr(), sh.data_ptr(),
+                                                 mu.data_ptr(), isd.data_ptr(), units, g.data_ptr(), acc.t.data_ptr(), st))
+            torch.cuda.synchronize()
+            assert acc.intact() and bool(torch.isfinite(acc.t).all()), (variant, units)
+        torch.cuda.synchronize()
+        assert mom.intact() and float(mom.t[0]) != SENT_F
+    # four clouds at the 0.05 m SECOND grid: automatic hash table
+    F, V, T = 4, 5000, 5
+    frames = [synth.c5_frame(600 + f)[:25000] for f in range(F)]
+    pts = torch.from_numpy(np.concatenate(frames)).to(dev)
+    offs = np.arange(F + 1, dtype=np.int64) * 25000
+    cfg = make_cfg(synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, T, V, 4, "continue", True)
+    vox = Guarded((F, V, T, 4), torch.float32, dev)
+    co = Guarded((F, V, 3), torch.int32, dev)
+    num = Guarded((F, V), torch.int32, dev)
+    vnum = Guarded((F,), torch.int32, dev)
+    nat.check(lib.lv_voxelize(h.ptr, ctypes.byref(cfg), pts.data_ptr(), F, offs.ctypes.data, vox.t.data_ptr(), co.t.data_ptr(),
+                              num.t.data_ptr(), vnum.t.data_ptr(), st))
+    torch.cuda.synchronize()
+    for g_ in (vox, co, num, vnum):
+        assert g_.intact()
+    assert int(vnum.t.min()) > 0 and int(vnum.t.max()) <= V
