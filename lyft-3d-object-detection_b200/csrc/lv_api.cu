@@ -189,6 +189,14 @@ int lv_set_option(lv_handle* h, const char* name, int64_t value) {
     h->vox_generic_rows = value;
     return LV_OK;
   }
+  if (strcmp(name, "vox_small_bins") == 0) {
+    h->vox_small_bins = value;
+    return LV_OK;
+  }
+  if (strcmp(name, "vox_two_level_scan") == 0) {
+    h->vox_two_level_scan = value;
+    return LV_OK;
+  }
   if (strcmp(name, "vox_hash_map") == 0) {
     h->vox_hash_map = value;
     return LV_OK;

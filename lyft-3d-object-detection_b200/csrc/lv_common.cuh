@@ -92,6 +92,9 @@ struct lv_handle {
                                       // look-back and polling instead of kernel boundaries).  Off by default: bit-identical, but measured
                                       // slower (0.724 vs 0.671 ms per 128 pillar frames; see the kernel's header in lv_voxel.cu)
   int64_t vox_generic_rows = 0;       // 1: the fused decoration always runs the generic row writer (A/B against the T = 60 / 9-channel one)
+  int64_t vox_small_bins = 0;         // -1: never shrink the bins of K6 for calls with few frames (A/B)
+  int64_t vox_two_level_scan = 0;     // K4: 0 = automatic (two levels when a frame's [bin][chunk] table exceeds 16 k counters),
+                                      // 1 = always, -1 = never
   int64_t vox_hash_map = 0;           // first[] as an open-addressing table sized by the points instead of a dense map sized by the
                                       // grid: 0 = automatic (grids whose dense map exceeds 48 MB per frame), 1 = always, -1 = never
   int64_t vox_rows_waves = 0;         // CTAs of vl_rows_kernel per resident slot (0 = 4)

@@ -89,6 +89,8 @@ struct VoxParams {
   int32_t* frame_cut;          // [frames] break cut-off (local index)
   int32_t* frame_kept;         // [frames] kept points
   int32_t* bin_start;          // [frames][n_bins + 1] first list position of every bin of a frame (+ the kept total)
+  int two_level_scan;          // 1: hist rows hold positions RELATIVE to their bin's start (large frames: one CTA per (frame, bin)
+                               //    scans its row, one per frame scans the bin totals); 0: absolute positions (one CTA per frame)
   unsigned* frame_sync;        // [frames][2] arrival counters of the fused prologue (all zero between calls)
   int* err;                    // device flag: a bounded spin of the fused prologue gave up
   // outputs
@@ -432,6 +434,32 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scan_hist_kernel(VoxParams p) {
   if (threadIdx.x == 0) bstart[p.n_bins] = total;
 }
 
+// K4 in two levels for frames with many chunks (a 1.06 M-point cloud has 519: one CTA would scan 30-120 k counters
+// alone): grid (n_bins, frames) - every CTA scans the chunk row of ITS bin in place and leaves the bin's total in
+// bin_start[bin]; then one CTA per frame turns the totals into bin starts.  K5 adds the two.
+__global__ void __launch_bounds__(VX_THREADS) vx_scan_rows_kernel(VoxParams p) {
+  __shared__ int sw[VX_WARPS];
+  __shared__ int carry;
+  const int d = blockIdx.x, fl = blockIdx.y, f = p.f0 + fl;
+  const int cb = __ldg(p.frame_chunk + f) - p.chunk_lo;
+  const int nch = __ldg(p.frame_chunk + f + 1) - __ldg(p.frame_chunk + f);
+  const int total = nch > 0 ? vx_cta_exclusive_scan(p.hist + (int64_t)cb * p.n_bins + (int64_t)d * nch, nch, sw, &carry) : 0;
+  if (threadIdx.x == 0) p.bin_start[(int64_t)fl * (p.n_bins + 1) + d] = total;
+}
+__global__ void __launch_bounds__(VX_THREADS) vx_scan_bins_kernel(VoxParams p) {
+  __shared__ int sw[VX_WARPS];
+  __shared__ int carry;
+  const int fl = blockIdx.x, f = p.f0 + fl;
+  const int nch = __ldg(p.frame_chunk + f + 1) - __ldg(p.frame_chunk + f);
+  int32_t* bstart = p.bin_start + (int64_t)fl * (p.n_bins + 1);
+  const int total = vx_cta_exclusive_scan(bstart, p.n_bins, sw, &carry);
+  if (threadIdx.x == 0) {
+    bstart[p.n_bins] = total;
+    p.frame_kept[fl] = total;
+    if (nch == 0) p.voxel_num[f] = 0;  // a frame without points never ran K2
+  }
+}
+
 // ---------------------------------------------------------------- K5: stable multi-split into bins
 // Warp w owns items [w*256, (w+1)*256) of the chunk in 8 rounds of 32 lanes, so
 // (warp, round, lane) order is point order.  Per-warp bin counters live in shared memory;
@@ -486,8 +514,10 @@ __global__ void __launch_bounds__(VX_THREADS) vx_scatter_kernel(VoxParams p) {
   }
   __syncthreads();
   const int32_t* tab = p.hist + (int64_t)(__ldg(p.frame_chunk + L.f) - p.chunk_lo) * D;
+  const int32_t* bstart = p.bin_start + (int64_t)L.fl * (D + 1);
   for (int d = threadIdx.x; d < D; d += VX_THREADS) {
     int off = tab[(int64_t)d * L.nchunks + L.c];
+    if (p.two_level_scan) off += bstart[d];
 #pragma unroll
     for (int w = 0; w < VX_WARPS; ++w) {
       const int t = cnt[w * D + d];
@@ -1531,6 +1561,12 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
   int L = VX_MAX_LOW_BITS;
   while (L > 0 && ((size_t)1 << L) * T * 4 > 32 * 1024) --L;
   while ((((int64_t)V + (1 << L) - 1) >> L) > VX_MAX_BINS && L < 20) ++L;
+  // few frames per call (a single ten-sweep cloud): one CTA per (frame, bin) leaves most SMs idle in K6, so the bins shrink
+  // until the call has ~4 CTAs per SM or 512 bins per frame (every bin costs K3-K5 a counter per chunk)
+  if (h->vox_small_bins >= 0)
+    while (L > 5 && (int64_t)n_frames * (((int64_t)V + (1 << L) - 1) >> L) < 4ll * h->num_sms &&
+           (((int64_t)V + (1 << (L - 1)) - 1) >> (L - 1)) <= 512)
+      --L;
   const int n_bins = (int)(((int64_t)V + (1 << L) - 1) >> L);
   const int NV = 1 << L;
   const size_t deco_stage = pfn ? (size_t)VX_WARPS * T * LV_PFN_STRIDE * 4
@@ -1719,6 +1755,13 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
     const int64_t pt_lo = h_frame_offsets[f0], npts = h_frame_offsets[f1] - pt_lo;
     const int chunk_lo = frame_chunk[f0], nchunks = frame_chunk[f1] - chunk_lo;
     p.f0 = f0; p.f1 = f1; p.chunk_lo = chunk_lo; p.pt_lo = pt_lo;
+    {   // frames with many chunks: the [bin][chunk] table of one frame is too long for one CTA to scan
+      int max_ch = 0;
+      for (int f = f0; f < f1; ++f)
+        if (frame_chunk[f + 1] - frame_chunk[f] > max_ch) max_ch = frame_chunk[f + 1] - frame_chunk[f];
+      p.two_level_scan = (int64_t)max_ch * n_bins > 16384 && h->vox_two_level_scan >= 0 ? 1 : 0;
+      if (h->vox_two_level_scan == 1) p.two_level_scan = 1;
+    }
 
     if (list_path) {
       LV_CHECK(h->vox_map.ensure((size_t)nf * G * 8, stream, 0x7f));
@@ -1861,7 +1904,13 @@ static int vx_run(lv_handle* h, const lv_voxel_config* cfg, const float* d_point
         vx_keys_kernel<<<nchunks, VX_THREADS, smem_keys, stream>>>(p);
         LV_LAUNCH_CHECK(h);
       }
-      vx_scan_hist_kernel<<<nf, VX_THREADS, 0, stream>>>(p);
+      if (p.two_level_scan) {
+        vx_scan_rows_kernel<<<dim3((unsigned)n_bins, (unsigned)nf), VX_THREADS, 0, stream>>>(p);
+        LV_LAUNCH_CHECK(h);
+        vx_scan_bins_kernel<<<nf, VX_THREADS, 0, stream>>>(p);
+      } else {
+        vx_scan_hist_kernel<<<nf, VX_THREADS, 0, stream>>>(p);
+      }
       LV_LAUNCH_CHECK(h);
       if (nchunks > 0) {
         vx_scatter_kernel<<<nchunks, VX_THREADS, smem_scatter, stream>>>(p);

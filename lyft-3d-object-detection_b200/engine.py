@@ -38,7 +38,8 @@ ENV_OPTIONS = {"LV_VOX_MAP_MB": ("vox_dense_map_limit_bytes", 1 << 20), "LV_BEV_
                "LV_VOX_FRAME_KERNEL": ("vox_frame_kernel", 1), "LV_VOX_LIST_PATH": ("vox_list_path", 1),
                "LV_VOX_ROWS_WAVES": ("vox_rows_waves", 1), "LV_VOX_FUSED": ("vox_fused_prologue", 1),
                "LV_BEV_FUSED_ZERO": ("bev_fused_zero", 1), "LV_VOX_HASH": ("vox_hash_map", 1),
-               "LV_BEV_U16": ("bev_u16", 1), "LV_VOX_GENERIC_ROWS": ("vox_generic_rows", 1)}
+               "LV_BEV_U16": ("bev_u16", 1), "LV_VOX_GENERIC_ROWS": ("vox_generic_rows", 1),
+               "LV_VOX_SCAN2": ("vox_two_level_scan", 1), "LV_VOX_SMALL_BINS": ("vox_small_bins", 1)}
 
 
 def apply_env_options(handle):

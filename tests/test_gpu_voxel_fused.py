@@ -162,3 +162,32 @@ def test_hash_table_equals_dense_map_and_oracle(env, mode):
             assert np.array_equal(outs[1][1][f, :k].cpu().numpy(), c)
             assert np.array_equal(outs[1][2][f, :k].cpu().numpy(), n)
             assert np.array_equal(outs[1][0][f, :k].cpu().numpy().view(np.uint32), v.view(np.uint32))
+
+
+def test_two_level_bin_scan_equals_single_cta_scan(env):
+    """K4 in two levels (one CTA per (frame, bin) row, then one per frame; automatic when a frame's [bin][chunk] table
+    exceeds 16 k counters, i.e. for 1 M-point clouds) == the single-CTA scan: forced on and off on small ragged frames,
+    an empty frame, both overflow rules, and on a 584 k-point cloud where it is the default."""
+    torch, nat, vg, vo = env
+    h = nat.get_handle(0)
+    sizes = [53146, 0, 1, 2049, 70000]
+    frames = _frames(sizes)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    big = torch.from_numpy(synth.multisweep_cloud(11)).cuda()
+    boffs = np.array([0, big.shape[0]], dtype=np.int64)
+    for mode in ("continue", "break"):
+        for p_, o_, vs, rg, T, V in ((pts, offs, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000),
+                                     (pts, offs, synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, 3000),
+                                     (big, boffs, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000),
+                                     (big, boffs, synth.SECOND_VOXEL_SIZE, synth.SECOND_RANGE, 5, 60000)):
+            outs = []
+            for opt in (-1, 1, 0):
+                h.set_option("vox_two_level_scan", opt)
+                try:
+                    outs.append(vg.voxelize_frames(p_, o_, vs, rg, T, V, overflow=mode, zero_tail=True))
+                finally:
+                    h.set_option("vox_two_level_scan", 0)
+            for o in outs[1:]:
+                for x, y in zip(outs[0], o):
+                    assert torch.equal(x, y), (mode, T)
