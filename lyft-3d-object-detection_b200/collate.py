@@ -32,7 +32,6 @@ from collections import defaultdict
 
 import numpy as np
 
-from . import _native as nat
 from .voxel_generator import VoxelGeneratorV2, voxelize_concat_frames, voxelize_frames
 
 POINT_OFFSETS_KEY = "point_offsets"
@@ -202,4 +201,3 @@ def example_convert_to_torch(example, dtype=None, device=None, voxel_generator=N
 
 __all__ = ["RawPoints", "DeferredVoxelGenerator", "merge_second_batch", "merge_second_batch_multigpu",
            "example_convert_to_torch", "POINT_OFFSETS_KEY"]
-_ = nat  # the module has no CPU fallback: the first deferred batch loads the CUDA library

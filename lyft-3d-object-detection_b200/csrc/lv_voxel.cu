@@ -149,13 +149,13 @@ __device__ __forceinline__ int vx_hash_insert(int32_t* tab, int bits, int cell, 
   unsigned h = ((unsigned)cell * 2654435761u) >> (32 - bits);
   const unsigned long long mine = ((unsigned long long)(unsigned)cell << 32) | (unsigned)li;
   while (true) {
-    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(t + h);
-    if (cur == VX_EMPTY64) {
-      cur = atomicCAS(t + h, VX_EMPTY64, mine);
-      if (cur == VX_EMPTY64) return (int)h;
-    }
+    // one round trip per probe: the CAS claims an empty slot and otherwise returns what is there; a slot that already
+    // belongs to the cell only needs the atomicMin when it holds a LARGER index (points arrive roughly in index order,
+    // so mostly it does not)
+    const unsigned long long cur = atomicCAS(t + h, VX_EMPTY64, mine);
+    if (cur == VX_EMPTY64) return (int)h;
     if ((unsigned)(cur >> 32) == (unsigned)cell) {
-      atomicMin(t + h, mine);
+      if (mine < cur) atomicMin(t + h, mine);
       return (int)h;
     }
     h = (h + 1) & mask;
