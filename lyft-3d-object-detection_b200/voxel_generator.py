@@ -251,6 +251,36 @@ class VoxelGeneratorV2:
         voxels, coords, num, k = self._run(points, max_voxels, padded=True)
         return {"voxels": voxels, "coordinates": coords, "num_points_per_voxel": num, "voxel_num": k}
 
+    def generate_batch(self, clouds, max_voxels=None):
+        """``[self.generate(c, max_voxels) for c in clouds]`` for host numpy clouds in ONE pass: one copy of all the
+        points to the device, one run of the kernels over all the clouds (lv_voxelize_host_begin), then the rows of every
+        cloud (lv_voxelize_host_fetch) - the launch and synchronisation cost of a call is paid once per batch instead of
+        once per sweep."""
+        clouds = [np.ascontiguousarray(c, dtype=np.float32) for c in clouds]
+        if not clouds:
+            return []
+        if any(c.ndim != 2 or c.shape[1] != clouds[0].shape[1] for c in clouds):
+            raise ValueError("clouds must be (N_i, C) arrays with the same C")
+        mv = self._max_voxels if max_voxels is None else int(max_voxels)
+        lib = nat.load()
+        C, T, F = clouds[0].shape[1], self._max_num_points, len(clouds)
+        pts = np.concatenate(clouds, axis=0)
+        offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int64)
+        cfg = _make_config(self._voxel_size, self._point_cloud_range, T, mv, C, self._overflow, False)
+        vnum = np.zeros((F,), dtype=np.int32)
+        h = nat.get_handle()
+        flt = _make_filter(self._block_filter) if self._block_filter is not None else None
+        nat.check(lib.lv_voxelize_host_begin(h.ptr, ctypes.byref(cfg), ctypes.byref(flt) if flt is not None else None,
+                                             pts.ctypes.data, F, offs.ctypes.data, vnum.ctypes.data))
+        out = []
+        for f in range(F):
+            k = int(vnum[f])
+            voxels, coords, num = _pinned_empty((k, T, C), np.float32), _pinned_empty((k, 3), np.int32), \
+                _pinned_empty((k,), np.int32)
+            nat.check(lib.lv_voxelize_host_fetch(h.ptr, f, k, voxels.ctypes.data, coords.ctypes.data, num.ctypes.data))
+            out.append({"voxels": voxels, "coordinates": coords, "num_points_per_voxel": num, "voxel_num": k})
+        return out
+
     @property
     def voxel_size(self):
         return self._voxel_size

@@ -72,6 +72,40 @@ def decorate(voxels, num_points, coors, voxel_size, pc_range, variant="pfn", wit
     return feats * mask
 
 
+def decorate_mismatch(out, ref, voxels, num_points, variant="pfn", with_distance=False):
+    """Compares a decoration `out` with the reference `ref`; returns (ok, worst, max_abs):
+      * channels that are copies or ONE subtraction (x, y, z, r, f_center, height): must be equal;
+      * norms (radius, distance): 1e-6 relative (BASELINE.json north_star);
+      * f_cluster = x - mean: the float32 sum over T is the one freedom of the op (torch's own CPU and CUDA sums differ
+        the same way).  ANY two correctly rounded summation orders of n values differ by at most 2 (n-1) u sum|x|
+        (u = 2^-24; Higham, Accuracy and Stability of Numerical Algorithms, (4.4)); the mean divides that by n, and the
+        division and the subtraction add one ulp each.  ok requires every value inside this bound
+            B = 2 u sum|x| (n-1)/n + ulp(sum|x| / n) + ulp(max|x|)
+        `worst` is the largest error as a fraction of B, `max_abs` the largest absolute f_cluster error.  Measured
+        against this numpy oracle over frames 0..255 and 1024..1031 of the C5 set (tools/verify_frames.py): max_abs
+        1.14e-5 (e.g. a pillar of 14 points 46.9 m out; a fixed atol of 1e-5 fails on such pillars), worst 0.70 of B."""
+    out, ref = np.asarray(out), np.asarray(ref)
+    if out.shape != ref.shape:
+        return False, float("inf"), float("inf")
+    k = 4 if variant in ("pfn", "old") else 3
+    cl = [k, k + 1, k + 2]
+    norms = ([0] if variant in ("radius", "radius_height") else []) + ([ref.shape[2] - 1] if with_distance else [])
+    rest = [c for c in range(ref.shape[2]) if c not in cl and c not in norms]
+    ok = bool(np.array_equal(out[..., rest], ref[..., rest]))
+    if norms:
+        ok = ok and bool(np.allclose(out[..., norms], ref[..., norms], rtol=1e-6, atol=0))
+    num = np.maximum(np.asarray(num_points), 1).astype(np.float64)[:, None]
+    mask = np.arange(ref.shape[1])[None, :] < np.asarray(num_points)[:, None]
+    v3 = np.abs(np.asarray(voxels, dtype=np.float32)[..., :3])
+    ssum = v3.sum(axis=1, dtype=np.float64)
+    bound = (2.0 ** -23 * ssum * (num - 1) / num + np.spacing((ssum / num).astype(np.float32)) + np.spacing(v3.max(axis=1)))[:, None, :]
+    err = np.abs(out[..., cl].astype(np.float64) - ref[..., cl].astype(np.float64))
+    worst = float((err / bound)[mask].max()) if mask.any() else 0.0
+    max_abs = float(err[mask].max()) if mask.any() else 0.0
+    pad_ok = bool((out[..., cl][~mask] == ref[..., cl][~mask]).all())
+    return ok and pad_ok and worst <= 1.0, worst, max_abs
+
+
 def scatter(voxel_features, coords, batch_size, ny, nx):
     """PointPillarsScatter.forward, pointpillars.py:444-476 -> (B,C,ny,nx)."""
     feats = np.asarray(voxel_features)

@@ -59,7 +59,10 @@ def test_fused_pillarize_equals_voxelize_then_decorate(setup):
     res = [orc.generate(fr) for fr in frames]
     ref = po.decorate(np.concatenate([r[0] for r in res]), np.concatenate([r[2] for r in res]),
                       po.merge_batch_coords([r[1] for r in res]), synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE)
-    np.testing.assert_allclose(fused.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    ok, worst, max_abs = po.decorate_mismatch(fused.cpu().numpy(), ref, np.concatenate([r[0] for r in res]),
+                                              np.concatenate([r[2] for r in res]))
+    print("fused decoration vs oracle: f_cluster max abs diff %.3g, %.3f of the summation-order bound" % (max_abs, worst))
+    assert ok and max_abs <= 2e-5, (worst, max_abs)
 
 
 def test_full_step_vs_cpu_path(setup):
@@ -317,3 +320,24 @@ def test_fused_pillarize_small_max_points(T):
     ref = pp.pillar_pfn(eng.voxels[:rows], eng.num_points[:rows], eng.coords[:rows], net.vx, net.vy, net.x_offset,
                         net.y_offset, w, sc, sh)
     assert bool((fused == ref).all())
+
+
+def test_decoration_bound_holds_on_the_frame_that_fails_a_fixed_atol():
+    """synth.c5_frame(1031) holds a pillar of 14 points 46.9 m from the sensor whose f_cluster differs from the numpy
+    oracle by 1.14e-5 = 3 ulp(46.9 m) - more than a fixed atol of 1e-5, a fraction of what two float32 summation
+    orders of 14 such values may differ by (oracle/pillar_oracle.py::decorate_mismatch).  Found by bench.py's post-run
+    check on rank 7 of an 8-GPU run; every other output of the frame is bit-exact."""
+    import torch
+    from lyft3d_b200.engine import FrameBatchEngine
+    from oracle import pillar_oracle as po, voxel_oracle as vo
+    fr = synth.c5_frame(1031)
+    eng = FrameBatchEngine(0, 1, fr.shape[0])
+    eng.pillarize(torch.from_numpy(fr).cuda())
+    rows = eng.read_total_rows()
+    v, c, n = vo.points_to_voxel(fr, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)
+    assert rows == v.shape[0] and np.array_equal(eng.coords[:rows, 1:].cpu().numpy(), c)
+    ref = po.decorate(v, n, po.merge_batch_coords([c]), synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE)
+    got = eng.decorated[:rows].cpu().numpy()
+    ok, worst, max_abs = po.decorate_mismatch(got, ref, v, n)
+    print("frame 1031: f_cluster max abs diff %.3g = %.3f of the summation-order bound" % (max_abs, worst))
+    assert ok and 1e-5 < max_abs <= 2e-5

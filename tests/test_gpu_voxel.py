@@ -314,3 +314,20 @@ def test_cluster_frame_kernel_equals_the_five_kernel_prologue(vg, vo, mode):
             h.set_option("vox_frame_kernel", 0)
     for a, b in zip(res[0], res[1]):
         assert torch.equal(a, b)
+
+
+def test_generate_batch_equals_generate_per_cloud(vg):
+    """VoxelGeneratorV2.generate_batch: several host clouds in one pass == generate() on each (also with the block filter)."""
+    clouds = [synth.c5_frame(70 + i)[: 20000 + 9000 * i] for i in range(4)] + [np.zeros((0, 4), np.float32)]
+    for kw in ({}, dict(block_filtering=True, block_factor=1, block_size=8, height_threshold=0.2)):
+        vs, rg, T, V = ((0.05, 0.05, 0.2), (-50, -50, -5, 50, 50, 3), 3, 20000) if kw else (synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, 30000)
+        gen = vg.VoxelGeneratorV2(vs, rg, T, max_voxels=V, **kw)
+        batch = gen.generate_batch(clouds, V)
+        assert len(batch) == len(clouds)
+        for c, b in zip(clouds, batch):
+            one = gen.generate(c, V)
+            assert b["voxel_num"] == one["voxel_num"]
+            for key in ("voxels", "coordinates", "num_points_per_voxel"):
+                assert b[key].dtype == one[key].dtype and b[key].shape == one[key].shape
+                assert np.array_equal(b[key].view(np.uint8), one[key].view(np.uint8)), key
+    assert gen.generate_batch([]) == []

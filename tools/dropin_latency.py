@@ -34,6 +34,11 @@ def main():
         ora = voxel_oracle.VoxelOracle(vs, rg, T, V)
         cpu = wall(lambda: ora.generate(pts), reps=3)
         print("%-48s generate(): %.3f ms   CPU oracle (C, 1 core): %.2f ms" % (name, ms, cpu))
+    # sixteen sweeps per call through generate_batch: launches and synchronisation paid once per batch
+    gen = vg.VoxelGeneratorV2(synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 60, max_voxels=30000)
+    sweeps = [synth.c5_frame(f) for f in range(16)]
+    ms = wall(lambda: gen.generate_batch(sweeps, 30000))
+    print("%-48s generate_batch(16 sweeps): %.3f ms = %.3f ms per sweep" % ("C3 pillars 0.25 m, 53,146 points each", ms, ms / 16))
 
 
 if __name__ == "__main__":
