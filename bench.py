@@ -41,14 +41,16 @@ def workload_cfg():
 
 
 def config_json(frames_per_step, n_gpus, extra=None):
+    """The workload both arms of the bench run (BASELINE.json configs[4]); identical for `--impl native` and
+    `--impl reference` at the same --gpus / --frames-per-step (what differs between the arms - the execution, the
+    bounded sample of the CPU arm - is reported beside it, not inside it)."""
     c = {"workload": "C5 throughput sweep: synthetic 53,146-point Lyft sweeps, BEV 336x336x3 (norm f32 + u8) "
                      "+ pillar path (voxelize 0.25 m/T=60/V=30000 -> decorate -> scatter 64x400x400)",
          "pillar_path": "fused voxelize+decorate" if not (extra or {}).get("unfused") else "separate voxelize, decorate",
          "frames_per_step_per_gpu": frames_per_step, "points_per_frame": 53146,
          "parallelism": "frames sharded f mod G, dp%d, no collective" % n_gpus,
+         "frames": "synth.c5_frame(f): the seeded definition of configs[4] the parity tests use, frame f on rank f mod G",
          "l2": "inputs (pool of distinct frames) and outputs per step exceed the 126 MB L2"}
-    if extra:
-        c.update(extra)
     return c
 
 
@@ -480,7 +482,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_sec / max(args.steps, 1) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 coords, u32 counts",
-            "data": "synthetic", "config": config_json(per_step, args.gpus, {"sample": sample}),
+            "data": "synthetic", "config": config_json(args.frames_per_step, args.gpus),
+            "execution": "the oracle chain of oracle/cpu_path.py over a process pool on the host cores; every step is a "
+                         "bounded sample of the workload: " + sample,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -803,12 +807,11 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 points, f64 BEV affine, u32 counts",
                 "data": "synthetic",
-                "config": config_json(F, world, {
-                    "frames": "synth.c5_frame(f), f = rank (mod G): the seeded definition of configs[4] the parity tests use; "
-                              "a pool of %d frames per GPU is cycled (weak scaling)" % n_pool,
-                    "mean_pillars_per_frame": round(mean_rows / F, 1),
-                    "execution": "stages of neighbouring steps overlap on 3 streams (PipelinedEngine), no host sync"
-                                 if pipe_eng is not None else "one stream, stages back to back"}),
+                "config": config_json(F, world),
+                "frame_pool": "a pool of %d distinct frames per GPU is cycled (weak scaling); --strong walks the whole set" % n_pool,
+                "mean_pillars_per_frame": round(mean_rows / F, 1),
+                "execution": "stages of neighbouring steps overlap on 3 streams (PipelinedEngine), no host sync"
+                             if pipe_eng is not None else "one stream, stages back to back",
                 "roofline": roof, "stages": stage_info,
                 "one_stream_ms_per_step": round(serial_ms_total / args.steps, 4),
                 "pillar_path_with_fused_pfn": None if pfn_ms is None else {
