@@ -349,7 +349,7 @@ def time_reference_gpu_eager(eng, pts, reps=5):
     # a TRAINING step of the pillar feature net (pointpillars.py:203-231 + :51-65: decoration, Linear, BatchNorm1d with
     # batch statistics, ReLU, max; forward + backward for linear.weight, norm.weight, norm.bias) on 16 frames of the
     # batch: the reference's eager chain (it keeps the (P,60,9) and (P,60,64) tensors for autograd) beside the fused
-    # op (lv_pillar_pfn_moments + lv_pillar_pfn + lv_pillar_pfn_backward)
+    # op (lv_pillar_pfn_train_forward + lv_pillar_pfn_train_backward: five kernels)
     from lyft3d_b200 import pointpillars as pp, synth
     nsub = int(eng.voxel_offsets[min(16, eng.F)].item())
     vs_, ns_, cs_ = v[:nsub], num[:nsub], co[:nsub]

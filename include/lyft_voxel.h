@@ -405,6 +405,27 @@ int lv_pillar_pfn_backward(lv_handle* h, const float* d_voxels, const int32_t* d
                            const float* d_shift, const float* d_mean, const float* d_invstd, int32_t units,
                            const float* d_grad_out, double* d_acc, lv_stream stream);
 
+/* The two passes as complete operations (what lyft3d_b200.pointpillars._FusedPfnTrain binds): the 64-number ends
+ * - batch statistics from the moments; dW, dgamma, dbeta from the accumulators - run on the device too.
+ *   forward   d_out (P, units) = max over T of relu(BatchNorm_train(W f)); d_stats float [5][units] = scale
+ *             (gamma * invstd), shift (beta - mean * scale), batch mean, invstd, biased batch variance (the caller
+ *             updates running_mean / running_var from rows 2 and 4); d_moments float64 [C_out + C_out (C_out+1)/2]
+ *             is kept by the caller for the backward.
+ *   backward  d_dweight (units, C_out), d_dgamma (units), d_dbeta (units) for d_grad_out (P, units). */
+int lv_pillar_pfn_train_forward(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,
+                                const int32_t* d_coors, int64_t n_pillars, int32_t max_points, int32_t num_features,
+                                float vx, float vy, float x_offset, float y_offset, int32_t variant,
+                                int32_t with_distance, const float* d_weight, const float* d_gamma,
+                                const float* d_beta, double eps, int32_t units, float* d_out, float* d_stats,
+                                double* d_moments, lv_stream stream);
+int lv_pillar_pfn_train_backward(lv_handle* h, const float* d_voxels, const int32_t* d_num_points,
+                                 const int32_t* d_coors, int64_t n_pillars, int32_t max_points, int32_t num_features,
+                                 float vx, float vy, float x_offset, float y_offset, int32_t variant,
+                                 int32_t with_distance, const float* d_weight, const float* d_gamma, double eps,
+                                 const float* d_stats, const double* d_moments, int32_t units,
+                                 const float* d_grad_out, float* d_dweight, float* d_dgamma, float* d_dbeta,
+                                 lv_stream stream);
+
 /* lv_voxelize_concat + lv_pillar_pfn in one call: points in, (capacity_rows, units) pillar
  * features out (units == 64), ready for lv_pillar_scatter.  Replaces preprocess.py:299-317 +
  * :21-55, pointpillars.py:203-231 and :51-65 without writing voxels or decorated points. */

@@ -124,6 +124,8 @@ struct lv_handle {
   // multi-sweep ingest
   lv_mirror ing_offsets, ing_tm, ing_lag, ing_has;
 
+  lv_buffer pfn_acc;                  // training-mode PFN backward: float64 (units, 2 + C_in) accumulators
+
   // PNG encoder: look-back descriptors and records per CTA; *_host staging (images, files, sizes)
   lv_buffer png_state, png_rec, png_stage[3];
 };
@@ -138,7 +140,7 @@ inline std::vector<lv_buffer*> lv_all_buffers(lv_handle* h) {
           &h->vox_frame_offsets.dev, &h->vox_chunk_table.dev, &h->vox_chunk_frame.dev, &h->vox_stage_points, &h->vox_stage_out[0],
           &h->vox_stage_out[1], &h->vox_stage_out[2], &h->vox_stage_out[3], &h->flt_ranges, &h->flt_dst, &h->flt_tmp[0], &h->flt_tmp[1],
           &h->flt_tmp[2], &h->flt_tmp[3], &h->pil_map, &h->ing_offsets.dev,
-          &h->ing_tm.dev, &h->ing_lag.dev, &h->ing_has.dev, &h->png_state, &h->png_rec, &h->png_stage[0], &h->png_stage[1],
+          &h->ing_tm.dev, &h->ing_lag.dev, &h->ing_has.dev, &h->pfn_acc, &h->png_state, &h->png_rec, &h->png_stage[0], &h->png_stage[1],
           &h->png_stage[2]};
 }
 

@@ -267,3 +267,109 @@ extern "C" int lv_pillar_pfn_backward(lv_handle* h, const float* d_voxels, const
   LV_LAUNCH_CHECK(h);
   return LV_OK;
 }
+// ---------------------------------------------------------------- the 64-number ends of the two passes, on the device
+// moments -> batch statistics of y = W f over all N = P*T slots -> what lv_pillar_pfn and the backward kernel take.
+// stats: float [5][units] = scale (gamma * invstd), shift (beta - mean * scale), mean, invstd, biased variance.
+__global__ void pfn_train_stats_kernel(const double* __restrict__ mom, const float* __restrict__ w, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int cin, int units, double N, double eps,
+                                       float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= units) return;
+  const double* M = mom + cin;            // upper triangle, row by row
+  double mean = 0.0, ey2 = 0.0;
+  int e = 0;
+  for (int i = 0; i < cin; ++i) {
+    const double wi = (double)w[c * cin + i];
+    mean += wi * mom[i];
+    for (int j = i; j < cin; ++j, ++e) ey2 += (i == j ? 1.0 : 2.0) * wi * (double)w[c * cin + j] * M[e];
+  }
+  mean /= N;
+  ey2 /= N;
+  double var = ey2 - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double invstd = 1.0 / sqrt(var + eps);
+  const double scale = (double)gamma[c] * invstd;
+  stats[c] = (float)scale;
+  stats[units + c] = (float)((double)beta[c] - mean * scale);
+  stats[2 * units + c] = (float)mean;
+  stats[3 * units + c] = (float)invstd;
+  stats[4 * units + c] = (float)var;
+}
+
+// acc (dbeta, dgamma, A) + moments -> dW, dgamma, dbeta: the BatchNorm backward over all N slots written with the
+// moments (sum_live f = S1, sum_live yhat_c f = invstd_c (W M - mean S1)_c).  Statistics are recomputed in float64.
+__global__ void pfn_train_finish_kernel(const double* __restrict__ acc, const double* __restrict__ mom, const float* __restrict__ w,
+                                        const float* __restrict__ gamma, int cin, int units, double N, double eps,
+                                        float* __restrict__ d_w, float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= units) return;
+  const double* M = mom + cin;
+  double mean = 0.0, ey2 = 0.0;
+  int e = 0;
+  for (int i = 0; i < cin; ++i) {
+    const double wi = (double)w[c * cin + i];
+    mean += wi * mom[i];
+    for (int j = i; j < cin; ++j, ++e) ey2 += (i == j ? 1.0 : 2.0) * wi * (double)w[c * cin + j] * M[e];
+  }
+  mean /= N;
+  double var = ey2 / N - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double invstd = 1.0 / sqrt(var + eps);
+  const double* a = acc + (size_t)c * (2 + cin);
+  const double dbeta = a[0], dgamma = a[1];
+  d_beta[c] = (float)dbeta;
+  d_gamma[c] = (float)dgamma;
+  for (int k = 0; k < cin; ++k) {
+    double wm = 0.0;                       // (W M)[c, k], M symmetric
+    for (int l = 0; l < cin; ++l) {
+      const int i = l < k ? l : k, j = l < k ? k : l;
+      wm += (double)w[c * cin + l] * M[i * cin - i * (i - 1) / 2 + (j - i)];
+    }
+    const double yhat_f = invstd * (wm - mean * mom[k]);
+    d_w[c * cin + k] = (float)((double)gamma[c] * invstd * (a[2 + k] - dbeta / N * mom[k] - dgamma / N * yhat_f));
+  }
+}
+
+extern "C" int lv_pillar_pfn_train_forward(lv_handle* h, const float* d_voxels, const int32_t* d_num_points, const int32_t* d_coors,
+                                           int64_t n_pillars, int32_t max_points, int32_t num_features, float vx, float vy,
+                                           float x_offset, float y_offset, int32_t variant, int32_t with_distance,
+                                           const float* d_weight, const float* d_gamma, const float* d_beta, double eps,
+                                           int32_t units, float* d_out, float* d_stats, double* d_moments, lv_stream stream_) {
+  int c_out = 0;
+  LV_CHECK(pt_check("lv_pillar_pfn_train_forward", h, n_pillars, max_points, num_features, variant, with_distance, d_voxels, d_coors, &c_out));
+  LV_REQUIRE(units == 32 || units == 64 || units == 128, "lv_pillar_pfn_train_forward: units must be 32, 64 or 128, got %d", units);
+  LV_REQUIRE(n_pillars * (int64_t)max_points >= 2, "lv_pillar_pfn_train_forward: batch statistics need at least two slots");
+  LV_REQUIRE(d_weight && d_gamma && d_beta && d_out && d_stats && d_moments, "lv_pillar_pfn_train_forward: null pointer");
+  LV_CHECK(lv_pillar_pfn_moments(h, d_voxels, d_num_points, d_coors, n_pillars, max_points, num_features, vx, vy, x_offset, y_offset,
+                                 variant, with_distance, d_moments, stream_));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  pfn_train_stats_kernel<<<1, 128, 0, stream>>>(d_moments, d_weight, d_gamma, d_beta, c_out, units,
+                                                (double)n_pillars * (double)max_points, eps, d_stats);
+  LV_LAUNCH_CHECK(h);
+  return lv_pillar_pfn(h, d_voxels, d_num_points, d_coors, n_pillars, max_points, num_features, vx, vy, x_offset, y_offset, variant,
+                       with_distance, d_weight, d_stats, d_stats + units, units, d_out, stream_);
+}
+
+extern "C" int lv_pillar_pfn_train_backward(lv_handle* h, const float* d_voxels, const int32_t* d_num_points, const int32_t* d_coors,
+                                            int64_t n_pillars, int32_t max_points, int32_t num_features, float vx, float vy,
+                                            float x_offset, float y_offset, int32_t variant, int32_t with_distance,
+                                            const float* d_weight, const float* d_gamma, double eps, const float* d_stats,
+                                            const double* d_moments, int32_t units, const float* d_grad_out, float* d_dweight,
+                                            float* d_dgamma, float* d_dbeta, lv_stream stream_) {
+  int c_out = 0;
+  LV_CHECK(pt_check("lv_pillar_pfn_train_backward", h, n_pillars, max_points, num_features, variant, with_distance, d_voxels, d_coors, &c_out));
+  LV_REQUIRE(units == 32 || units == 64 || units == 128, "lv_pillar_pfn_train_backward: units must be 32, 64 or 128, got %d", units);
+  LV_REQUIRE(d_weight && d_gamma && d_stats && d_moments && d_grad_out && d_dweight && d_dgamma && d_dbeta,
+             "lv_pillar_pfn_train_backward: null pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LV_CHECK_CUDA(cudaSetDevice(h->device));
+  LV_CHECK(h->pfn_acc.ensure(sizeof(double) * 128 * (2 + 10), stream));
+  LV_CHECK(lv_pillar_pfn_backward(h, d_voxels, d_num_points, d_coors, n_pillars, max_points, num_features, vx, vy, x_offset, y_offset,
+                                  variant, with_distance, d_weight, d_stats, d_stats + units, d_stats + 2 * units, d_stats + 3 * units,
+                                  units, d_grad_out, h->pfn_acc.as<double>(), stream_));
+  pfn_train_finish_kernel<<<1, 128, 0, stream>>>(h->pfn_acc.as<double>(), d_moments, d_weight, d_gamma, c_out, units,
+                                                 (double)n_pillars * (double)max_points, eps, d_dweight, d_dgamma, d_dbeta);
+  LV_LAUNCH_CHECK(h);
+  return LV_OK;
+}
+

@@ -157,79 +157,58 @@ def pillar_pfn(features, num_voxels, coors, vx, vy, x_offset, y_offset, weight, 
     return out
 
 
-def _pfn_moments(features, num, coors, vx, vy, x_offset, y_offset, variant, with_distance, c_in):
-    """lv_pillar_pfn_moments -> (S1 (c_in), M (c_in, c_in)) float64: sums of f and f f^T over the live slots of
-    the decorated features."""
-    lib = nat.load()
-    n_tri = c_in * (c_in + 1) // 2
-    mom = torch.empty((c_in + n_tri,), dtype=torch.float64, device=features.device)
-    P, T, C = features.shape
-    h = nat.get_handle(features.device.index)
-    with torch.cuda.device(features.device):
-        nat.check(lib.lv_pillar_pfn_moments(h.ptr, features.data_ptr(), num.data_ptr(), coors.data_ptr(), P, T, C,
-                                            _f32(vx), _f32(vy), _f32(x_offset), _f32(y_offset),
-                                            nat.PILLAR_VARIANTS[variant], int(bool(with_distance)), mom.data_ptr(),
-                                            nat.current_stream_ptr(features.device)))
-    iu = torch.triu_indices(c_in, c_in, device=features.device)
-    M = torch.zeros((c_in, c_in), dtype=torch.float64, device=features.device)
-    M[iu[0], iu[1]] = mom[c_in:]
-    M = M + M.triu(1).T
-    return mom[:c_in], M
-
-
 class _FusedPfnTrain(torch.autograd.Function):
     """relu(BatchNorm1d_train(Linear(decorate(voxels)))) max-pooled over the points of a pillar
-    (pointpillars.py:51-65 behind :203-231) as ONE differentiable op on the CUDA library: neither the
-    (P,T,C_in) decorated tensor nor the (P,T,units) activations exist in HBM, in the forward or in the
-    backward.  Returns (out (P, units), batch mean (units), biased batch variance (units))."""
+    (pointpillars.py:51-65 behind :203-231) as ONE differentiable op on the CUDA library
+    (lv_pillar_pfn_train_forward / lv_pillar_pfn_train_backward): neither the (P,T,C_in) decorated tensor nor the
+    (P,T,units) activations exist in HBM, in the forward or in the backward, and the batch statistics and the
+    BatchNorm backward are computed on the device from float64 moments.
+    Returns (out (P, units), batch mean (units), biased batch variance (units))."""
 
     @staticmethod
     def forward(ctx, features, num, coors, weight, gamma, beta, eps, geom):
         vx, vy, xo, yo, variant, with_distance = geom
+        lib = nat.load()
         units, c_in = weight.shape
-        P, T, _ = features.shape
-        N = float(P * T)
-        S1, M = _pfn_moments(features, num, coors, vx, vy, xo, yo, variant, with_distance, c_in)
-        Wd = weight.detach().double()
-        mean = (Wd @ S1) / N
-        ey2 = torch.einsum("ck,kl,cl->c", Wd, M, Wd) / N
-        var = (ey2 - mean * mean).clamp_min(0.0)
-        invstd = torch.rsqrt(var + eps)
-        scale = gamma.detach().double() * invstd
-        shift = beta.detach().double() - mean * scale
-        scale_f, shift_f = scale.float().contiguous(), shift.float().contiguous()
+        P, T, C = features.shape
+        dev = features.device
         w_f = weight.detach().float().contiguous()
-        out = pillar_pfn(features, num, coors, vx, vy, xo, yo, w_f, scale_f, shift_f, variant=variant,
-                         with_distance=with_distance)
-        ctx.geom, ctx.N = geom, N
-        ctx.save_for_backward(features, num, coors, w_f, scale_f, shift_f, mean, invstd, S1, M, gamma.detach().double())
+        g_f, b_f = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        out = torch.empty((P, units), dtype=torch.float32, device=dev)
+        stats = torch.empty((5, units), dtype=torch.float32, device=dev)
+        mom = torch.empty((c_in + c_in * (c_in + 1) // 2,), dtype=torch.float64, device=dev)
+        h = nat.get_handle(dev.index)
+        with torch.cuda.device(dev):
+            nat.check(lib.lv_pillar_pfn_train_forward(
+                h.ptr, features.data_ptr(), num.data_ptr(), coors.data_ptr(), P, T, C, _f32(vx), _f32(vy), _f32(xo), _f32(yo),
+                nat.PILLAR_VARIANTS[variant], int(bool(with_distance)), w_f.data_ptr(), g_f.data_ptr(), b_f.data_ptr(),
+                float(eps), units, out.data_ptr(), stats.data_ptr(), mom.data_ptr(), nat.current_stream_ptr(dev)))
+        ctx.geom, ctx.eps = geom, float(eps)
+        ctx.save_for_backward(features, num, coors, w_f, g_f, stats, mom)
+        mean, var = stats[2], stats[4]
         ctx.mark_non_differentiable(mean, var)
         return out, mean, var
 
     @staticmethod
     def backward(ctx, grad_out, _gm, _gv):
-        features, num, coors, w_f, scale_f, shift_f, mean, invstd, S1, M, gamma = ctx.saved_tensors
+        features, num, coors, w_f, g_f, stats, mom = ctx.saved_tensors
         vx, vy, xo, yo, variant, with_distance = ctx.geom
+        lib = nat.load()
         units, c_in = w_f.shape
         P, T, C = features.shape
-        N = ctx.N
-        lib = nat.load()
+        dev = features.device
         g = grad_out.float().contiguous()
-        acc = torch.empty((units, 2 + c_in), dtype=torch.float64, device=features.device)
-        mean_f, invstd_f = mean.float().contiguous(), invstd.float().contiguous()
-        h = nat.get_handle(features.device.index)
-        with torch.cuda.device(features.device):
-            nat.check(lib.lv_pillar_pfn_backward(
-                h.ptr, features.data_ptr(), num.data_ptr(), coors.data_ptr(), P, T, C, _f32(vx), _f32(vy), _f32(xo),
-                _f32(yo), nat.PILLAR_VARIANTS[variant], int(bool(with_distance)), w_f.data_ptr(), scale_f.data_ptr(),
-                shift_f.data_ptr(), mean_f.data_ptr(), invstd_f.data_ptr(), units, g.data_ptr(), acc.data_ptr(),
-                nat.current_stream_ptr(features.device)))
-        dbeta, dgamma, A = acc[:, 0], acc[:, 1], acc[:, 2:]
-        # BatchNorm backward over all N slots, written with the moments: sum_live f = S1, sum_live yhat_c f = invstd_c (W M - mean S1)_c
-        Wd = w_f.double()
-        yhat_f = invstd[:, None] * (Wd @ M - mean[:, None] * S1[None, :])
-        dW = (gamma * invstd)[:, None] * (A - (dbeta / N)[:, None] * S1[None, :] - (dgamma / N)[:, None] * yhat_f)
-        return None, None, None, dW.float(), dgamma.float(), dbeta.float(), None, None
+        d_w = torch.empty((units, c_in), dtype=torch.float32, device=dev)
+        d_gamma = torch.empty((units,), dtype=torch.float32, device=dev)
+        d_beta = torch.empty((units,), dtype=torch.float32, device=dev)
+        h = nat.get_handle(dev.index)
+        with torch.cuda.device(dev):
+            nat.check(lib.lv_pillar_pfn_train_backward(
+                h.ptr, features.data_ptr(), num.data_ptr(), coors.data_ptr(), P, T, C, _f32(vx), _f32(vy), _f32(xo), _f32(yo),
+                nat.PILLAR_VARIANTS[variant], int(bool(with_distance)), w_f.data_ptr(), g_f.data_ptr(), ctx.eps,
+                stats.data_ptr(), mom.data_ptr(), units, g.data_ptr(), d_w.data_ptr(), d_gamma.data_ptr(), d_beta.data_ptr(),
+                nat.current_stream_ptr(dev)))
+        return None, None, None, d_w, d_gamma, d_beta, None, None
 
 
 class PFNLayer(nn.Module):

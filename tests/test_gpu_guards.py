@@ -205,6 +205,26 @@ def test_pfn_training_kernels_and_hash_table_outputs(env):
             assert acc.intact() and bool(torch.isfinite(acc.t).all()), (variant, units)
         torch.cuda.synchronize()
         assert mom.intact() and float(mom.t[0]) != SENT_F
+        # the two complete operations
+        units = 64
+        w = torch.randn((units, cout), device=dev)
+        gm, bt = torch.rand((units,), device=dev) + 0.5, torch.randn((units,), device=dev)
+        out = Guarded((P, units), torch.float32, dev)
+        stats = Guarded((5, units), torch.float32, dev)
+        mom2 = Guarded((cout + cout * (cout + 1) // 2,), torch.float64, dev)
+        nat.check(lib.lv_pillar_pfn_train_forward(h.ptr, v.data_ptr(), n.data_ptr(), c.data_ptr(), P, T, 4, 0.25, 0.25, -49.875,
+                                                  -49.875, variant, wd, w.data_ptr(), gm.data_ptr(), bt.data_ptr(), 1e-3, units,
+                                                  out.t.data_ptr(), stats.t.data_ptr(), mom2.t.data_ptr(), st))
+        g = torch.randn((P, units), device=dev)
+        dw, dg, db = Guarded((units, cout), torch.float32, dev), Guarded((units,), torch.float32, dev), Guarded((units,), torch.float32, dev)
+        nat.check(lib.lv_pillar_pfn_train_backward(h.ptr, v.data_ptr(), n.data_ptr(), c.data_ptr(), P, T, 4, 0.25, 0.25, -49.875,
+                                                   -49.875, variant, wd, w.data_ptr(), gm.data_ptr(), 1e-3, stats.t.data_ptr(),
+                                                   mom2.t.data_ptr(), units, g.data_ptr(), dw.t.data_ptr(), dg.t.data_ptr(),
+                                                   db.t.data_ptr(), st))
+        torch.cuda.synchronize()
+        for g_ in (out, stats, mom2, dw, dg, db):
+            assert g_.intact() and bool(torch.isfinite(g_.t).all()), variant
+        assert bool(torch.allclose(mom2.t, mom.t, rtol=1e-12, atol=1e-9))    # (float64 atomics: the order of the CTAs is free)
     # four clouds at the 0.05 m SECOND grid: automatic hash table
     F, V, T = 4, 5000, 5
     frames = [synth.c5_frame(600 + f)[:25000] for f in range(F)]

@@ -62,7 +62,7 @@ def test_fused_training_equals_reference_classes(pp, g, variant, wd, units):
     out = net(v, n, c)
     G = _cuda(g[tag + ".G"].astype(np.float32) / 64)
     (out * G).sum().backward()
-    assert pp.nat.get_handle(0).launches() - lib_launches == 3, "moments + forward + backward kernels expected"
+    assert pp.nat.get_handle(0).launches() - lib_launches == 5, "moments, statistics, forward, backward, finish kernels expected"
     got = dict(out=out.detach().cpu().numpy(), dW=layer.linear.weight.grad.cpu().numpy(),
                dgamma=layer.norm.weight.grad.cpu().numpy(), dbeta=layer.norm.bias.grad.cpu().numpy(),
                running_mean=layer.norm.running_mean.cpu().numpy(), running_var=layer.norm.running_var.cpu().numpy())
