@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32) pillar_moments_kernel(PtParams 
       const float* f = st + t * LV_PFN_STRIDE;
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
+        if (q == 2 && n_entries <= 64) break;   // C_in <= 9: 54 entries, two per lane
         const double fi = (double)f[mi[q]];
         const double fj = mj[q] == 255 ? 1.0 : (double)f[mj[q]];
         acc[q] = fma(fi, fj, acc[q]);
