@@ -331,3 +331,33 @@ def test_generate_batch_equals_generate_per_cloud(vg):
                 assert b[key].dtype == one[key].dtype and b[key].shape == one[key].shape
                 assert np.array_equal(b[key].view(np.uint8), one[key].view(np.uint8)), key
     assert gen.generate_batch([]) == []
+
+
+def test_gpu_voxelizer_against_the_reference_points_to_bev(vg, fixture_nx4, golden_dir):
+    """The GPU voxelizer pinned DIRECTLY to output of the reference's own code: the per-pillar point-count map that the
+    reference's in-tree sibling of the voxelizer (second/second/utils/simplevis.py:9-108, executed by oracle/gen_golden.py
+    into tests/golden/ref_simplevis_pillar.npz) draws for the bundled sweep - all 8,569 pillars / 47,732 points with
+    max_voxels=40000, and the `break` rule of :46-50 with max_voxels=3000 (3,000 pillars / 7,764 points).  The point
+    cap is set above the fullest pillar so that num_points_per_voxel is the count; the height map (highest point of
+    every pillar above the range floor, in units of the voxel height) follows from the voxels."""
+    g = np.load(os.path.join(golden_dir, "ref_simplevis_pillar.npz"))
+    T = 1024
+    assert int(g["density_full"].max()) < T
+    for V, mode, key, nvox, npts in ((40000, "continue", "density_full", 8569, 47732), (3000, "break", "density_break3000", 3000, 7764)):
+        voxels, coords, num, vnum = vg.voxelize_frames(fixture_nx4, np.array([0, fixture_nx4.shape[0]], dtype=np.int64),
+                                                       synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, T, V, overflow=mode,
+                                                       zero_tail=False)
+        k = int(vnum[0])
+        assert k == nvox and int(num[0][:k].sum()) == npts
+        dm = np.zeros((400, 400), np.int64)
+        dm[coords[0][:k, 1], coords[0][:k, 2]] = num[0][:k]
+        assert np.array_equal(dm, g[key].astype(np.int64)), key
+        if key == "density_full":
+            # simplevis.py:52-57: bev_map[0] = max over the pillar's points of (z - z_lo) / voxel height, where positive
+            vz = voxels[0][:k, :, 2]
+            live = np.arange(T)[None, :] < num[0][:k, None]
+            hn = ((vz - np.float32(synth.PILLAR_RANGE[2])) / np.float32(synth.PILLAR_VOXEL_SIZE[2])).astype(np.float32)
+            hmax = np.where(live, hn, -np.inf).max(axis=1)
+            hm = np.zeros((400, 400), np.float32)
+            hm[coords[0][:k, 1], coords[0][:k, 2]] = np.maximum(hmax, 0).astype(np.float32)
+            assert np.array_equal(hm, g["height_full"])
