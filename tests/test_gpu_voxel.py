@@ -361,3 +361,22 @@ def test_gpu_voxelizer_against_the_reference_points_to_bev(vg, fixture_nx4, gold
             hm = np.zeros((400, 400), np.float32)
             hm[coords[0][:k, 1], coords[0][:k, 2]] = np.maximum(hmax, 0).astype(np.float32)
             assert np.array_equal(hm, g["height_full"])
+
+
+def test_gpu_voxelizer_against_the_reference_points_to_bev_3d_grids(vg, golden_dir):
+    """The same pin at three-dimensional grids (tests/golden/ref_simplevis_3d.npz): counts per column, the highest
+    point of every (z, y, x) cell, and - through the `break` rule at small caps - which cells exist at all."""
+    from oracle import gen_golden_simplevis3d as gg
+    from oracle import voxel_oracle as vo
+    from test_oracle_voxel import _maps_from_voxels
+    g = np.load(os.path.join(golden_dir, "ref_simplevis_3d.npz"))
+    for name, first, n, vs, rg, mv in gg.CASES:
+        pts = gg.case_points(first, n)
+        T = 1024
+        assert int(g[name + ".count"].max()) < T
+        voxels, coords, num, vnum = vg.voxelize_frames(pts, np.array([0, n], dtype=np.int64), vs, rg, T, mv, overflow="break",
+                                                       zero_tail=False)
+        k = int(vnum[0])
+        count, height = _maps_from_voxels(voxels[0][:k], coords[0][:k], num[0][:k], vs, rg, vo.grid_size(vs, rg))
+        assert np.array_equal(count, g[name + ".count"].astype(np.int64)), name
+        assert np.array_equal(height, g[name + ".height"]), name

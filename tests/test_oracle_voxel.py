@@ -126,3 +126,32 @@ def test_upper_boundary_is_exclusive():
                     [0, 0, 10.0, 0], [0, 0, -10.0, 0]], np.float32)
     v, c, n = vo.points_to_voxel(pts, synth.PILLAR_VOXEL_SIZE, synth.PILLAR_RANGE, 5, 100)
     assert c.tolist() == [[0, 200, 399], [0, 200, 0], [0, 200, 200]]
+
+
+def _maps_from_voxels(voxels, coords, num, vs, rg, grid):
+    """What simplevis.points_to_bev draws (:52-57), rebuilt from a voxelizer's output with an uncapped point list:
+    count per (y, x) column and, per (z, y, x) cell, the highest point above the slice floor in slice heights."""
+    gx, gy, gz = (int(v) for v in grid)
+    count = np.zeros((gy, gx), np.int64)
+    np.add.at(count, (coords[:, 1], coords[:, 2]), num)
+    lowers = np.linspace(np.float32(rg[2]), np.float32(rg[5]), gz, endpoint=False).astype(np.float32)
+    T = voxels.shape[1]
+    live = np.arange(T)[None, :] < num[:, None]
+    hn = ((voxels[:, :, 2] - lowers[coords[:, 0]][:, None]) / np.float32(vs[2])).astype(np.float32)
+    hmax = np.where(live, hn, -np.inf).max(axis=1) if voxels.shape[0] else np.zeros((0,), np.float32)
+    height = np.zeros((gz, gy, gx), np.float32)
+    height[coords[:, 0], coords[:, 1], coords[:, 2]] = np.maximum(hmax, 0).astype(np.float32)
+    return count, height
+
+
+def test_against_reference_points_to_bev_3d_grids(golden_dir):
+    """tests/golden/ref_simplevis_3d.npz (oracle/gen_golden_simplevis3d.py ran the reference's points_to_bev): grids
+    with several height slices, caps hit early (the `break` rule decides which cells exist, i.e. first-come order)."""
+    from oracle import gen_golden_simplevis3d as gg
+    g = np.load(os.path.join(golden_dir, "ref_simplevis_3d.npz"))
+    for name, first, n, vs, rg, mv in gg.CASES:
+        pts = gg.case_points(first, n)
+        v, c, k = vo.points_to_voxel(pts, vs, rg, 4096, mv, overflow="break")
+        count, height = _maps_from_voxels(v, c, k, vs, rg, vo.grid_size(vs, rg))
+        assert np.array_equal(count, g[name + ".count"].astype(np.int64)), name
+        assert np.array_equal(height, g[name + ".height"]), name
