@@ -341,3 +341,38 @@ def test_decoration_bound_holds_on_the_frame_that_fails_a_fixed_atol():
     ok, worst, max_abs = po.decorate_mismatch(got, ref, v, n)
     print("frame 1031: f_cluster max abs diff %.3g = %.3f of the summation-order bound" % (max_abs, worst))
     assert ok and 1e-5 < max_abs <= 2e-5
+
+
+def test_pipelined_soak_400_steps_leaves_every_workspace_clean():
+    """400 pipelined steps over four different batches without a single host synchronisation, then one more of
+    each batch checked bit for bit against the serial engine: the "all empty between calls" invariants of the
+    first[] map, the BEV counts and dirty bitmap and the cell->pillar map, and the two buffer sets of the pipeline,
+    survive a long run (a stale entry anywhere would show up as a wrong pillar, count or canvas cell)."""
+    import torch
+    from lyft3d_b200.engine import FrameBatchEngine, PipelinedEngine
+    F = 8
+    batches = []
+    for b in range(4):
+        frames = [synth.c5_frame(400 + 8 * b + f)[: 30000 + 2500 * ((b + f) % 5)] for f in range(F)]
+        n = 30000
+        batches.append(torch.from_numpy(np.concatenate([fr[:n] for fr in frames])).cuda())
+    eng = FrameBatchEngine(0, F, n)
+    torch.manual_seed(11)
+    eng.features.copy_(torch.randn_like(eng.features))
+    want = []
+    for pts in batches:
+        rows = eng.step(pts)
+        want.append((rows, eng.bev_u8.clone(), eng.bev_norm.clone(), eng.canvas.clone(), eng.coords[:rows].clone(),
+                     eng.num_points[:rows].clone(), eng.decorated[:rows].clone()))
+    pipe = PipelinedEngine(eng)
+    for i in range(400):
+        pipe.submit(batches[(i * 7) % 4])
+    for b, pts in enumerate(batches):
+        st = pipe.submit(pts)
+        pipe.drain()
+        torch.cuda.synchronize()
+        rows, u8, norm, canvas, coords, num, dec = want[b]
+        assert int(st["voxel_offsets"][F]) == rows
+        assert bool((eng.bev_u8 == u8).all()) and bool((eng.bev_norm == norm).all()) and bool((eng.canvas == canvas).all())
+        assert bool((st["coords"][:rows] == coords).all()) and bool((st["num_points"][:rows] == num).all())
+        assert bool((st["decorated"][:rows] == dec).all())
