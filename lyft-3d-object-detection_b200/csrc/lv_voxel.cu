@@ -140,13 +140,13 @@ __device__ __forceinline__ ChunkLoc vx_locate(const VoxParams& p) {
 // Open-addressing table for grids whose dense map would not stay in L2 (1056 x 1280 x 40 cells = 216 MB per cloud
 // for the 0.05 m SECOND config): 2^b slots of (value word, key word) per frame, a slot is claimed by a 64-bit CAS
 // of (cell id << 32 | point index) and lowered by a 64-bit atomicMin - the high word is equal, so the minimum is
-// the lowest point index.  Empty = every byte 0x7f, like the dense map.  Linear probing; the host sizes the table
-// at >= 1.25 x the points of the largest frame.  Returns the slot, which replaces the cell id in cell[].
+// the lowest point index.  Empty = every byte 0x7f, like the dense map.  Linear probing from slot `h` on (the home
+// slot is (cell * 2654435761) >> (32 - bits)); the host sizes the table at >= 1.25 x the points of the largest
+// frame.  Returns the slot, which replaces the cell id in cell[].
 #define VX_EMPTY64 0x7f7f7f7f7f7f7f7full
-__device__ __forceinline__ int vx_hash_insert(int32_t* tab, int bits, int cell, int li) {
+__device__ __forceinline__ int vx_hash_insert(int32_t* tab, int bits, int cell, int li, unsigned h) {
   unsigned long long* t = reinterpret_cast<unsigned long long*>(tab);
   const unsigned mask = (1u << bits) - 1u;
-  unsigned h = ((unsigned)cell * 2654435761u) >> (32 - bits);
   const unsigned long long mine = ((unsigned long long)(unsigned)cell << 32) | (unsigned)li;
   while (true) {
     // one round trip per probe: the CAS claims an empty slot and otherwise returns what is there; a slot that already
@@ -163,7 +163,7 @@ __device__ __forceinline__ int vx_hash_insert(int32_t* tab, int bits, int cell, 
 }
 
 template <bool C4, bool HASH>
-__global__ void __launch_bounds__(VX_THREADS) vx_cells_kernel(VoxParams p) {
+__global__ void __launch_bounds__(VX_THREADS, HASH ? 5 : 1) vx_cells_kernel(VoxParams p) {
   extern __shared__ __align__(128) float tile[];  // [VX_CHUNK][C] when p.tma_bytes != 0
   __shared__ __align__(8) uint64_t bar;
   const ChunkLoc L = vx_locate(p);
@@ -186,7 +186,13 @@ __global__ void __launch_bounds__(VX_THREADS) vx_cells_kernel(VoxParams p) {
     lv_mbar_wait(&bar, 0);
   }
   const int base = L.c * VX_CHUNK + warp * (32 * VX_ITEMS);
-#pragma unroll 2
+  // table form: the first probes of all eight rounds are issued before the first answer is looked at (eight CAS round
+  // trips in flight per thread instead of one after the other - the table of a batch of clouds does not stay in L2)
+  int h_cell[HASH ? VX_ITEMS : 1], h_lead[HASH ? VX_ITEMS : 1];
+  unsigned h_slot[HASH ? VX_ITEMS : 1];
+  unsigned long long h_cur[HASH ? VX_ITEMS : 1];
+  constexpr int UNROLL = HASH ? VX_ITEMS : 2;   // (the table form keeps its eight answers in registers)
+#pragma unroll UNROLL
   for (int r = 0; r < VX_ITEMS; ++r) {
     const int ti = warp * (32 * VX_ITEMS) + r * 32 + lane;  // row inside the chunk
     const int li = base + r * 32 + lane;                    // local point index inside the frame
@@ -219,12 +225,35 @@ __global__ void __launch_bounds__(VX_THREADS) vx_cells_kernel(VoxParams p) {
     const unsigned peers = __match_any_sync(0xffffffffu, cell);
     const int leader = __ffs(peers) - 1;
     if (HASH) {
-      int slot = -1;
-      if (cell >= 0 && lane == leader) slot = vx_hash_insert(map, p.hash_bits, cell, li);
-      slot = __shfl_sync(0xffffffffu, slot, leader);
-      if (li < L.n) p.cell[L.start + li - p.pt_lo] = cell >= 0 ? slot : -1;
+      h_cell[r] = cell;
+      h_lead[r] = leader;
+      h_slot[r] = ((unsigned)cell * 2654435761u) >> (32 - p.hash_bits);
+      h_cur[r] = 0ull;
+      if (cell >= 0 && lane == leader)
+        h_cur[r] = atomicCAS(reinterpret_cast<unsigned long long*>(map) + h_slot[r], VX_EMPTY64,
+                             ((unsigned long long)(unsigned)cell << 32) | (unsigned)li);
     } else if (cell >= 0 && lane == leader) {
       atomicMin(map + cell, li);
+    }
+  }
+  if (HASH) {
+#pragma unroll
+    for (int r = 0; r < VX_ITEMS; ++r) {
+      const int li = base + r * 32 + lane, cell = h_cell[r];
+      int slot = -1;
+      if (cell >= 0 && lane == h_lead[r]) {
+        const unsigned long long mine = ((unsigned long long)(unsigned)cell << 32) | (unsigned)li, cur = h_cur[r];
+        if (cur == VX_EMPTY64) {
+          slot = (int)h_slot[r];                       // claimed by the first probe
+        } else if ((unsigned)(cur >> 32) == (unsigned)cell) {
+          if (mine < cur) atomicMin(reinterpret_cast<unsigned long long*>(map) + h_slot[r], mine);
+          slot = (int)h_slot[r];
+        } else {                                       // collision: probe on from the next slot
+          slot = vx_hash_insert(map, p.hash_bits, cell, li, (h_slot[r] + 1) & ((1u << p.hash_bits) - 1u));
+        }
+      }
+      slot = __shfl_sync(0xffffffffu, slot, h_lead[r]);
+      if (li < L.n) p.cell[L.start + li - p.pt_lo] = cell >= 0 ? slot : -1;
     }
   }
 }
