@@ -426,6 +426,13 @@ int lv_pillar_pfn_train_backward(lv_handle* h, const float* d_voxels, const int3
                                  const float* d_grad_out, float* d_dweight, float* d_dgamma, float* d_dbeta,
                                  lv_stream stream);
 
+/* Backward of PointPillarsScatter (second/second/pytorch/models/pointpillars.py:444-476 under autograd):
+ * d_grad_feats (P, channels) [p, c] = d_grad_canvas (B, channels, ny, nx) [b, c, y, x] for coords[p] = (b, ., y, x); rows
+ * whose coordinates lie outside the canvas get zeros.  half != 0: both tensors are float16. */
+int lv_pillar_scatter_backward(lv_handle* h, const void* d_grad_canvas, const int32_t* d_coords, int64_t n_pillars,
+                               int32_t channels, int32_t batch_size, int32_t ny, int32_t nx, int32_t half,
+                               void* d_grad_feats, lv_stream stream);
+
 /* lv_voxelize_concat + lv_pillar_pfn in one call: points in, (capacity_rows, units) pillar
  * features out (units == 64), ready for lv_pillar_scatter.  Replaces preprocess.py:299-317 +
  * :21-55, pointpillars.py:203-231 and :51-65 without writing voxels or decorated points. */

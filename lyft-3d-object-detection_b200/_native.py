@@ -119,6 +119,7 @@ SIGNATURES = {
                                                    _vp, _vp, _vp, _f64, _i32, _vp, _vp, _vp, _vp]),
     "lv_pillar_pfn_train_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _i32, _i32,
                                                     _vp, _vp, _f64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "lv_pillar_scatter_backward": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lv_pillar_scatter": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lv_pillar_scatter_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lv_pillar_decorate_half": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _f32, _f32, _i32, _i32,

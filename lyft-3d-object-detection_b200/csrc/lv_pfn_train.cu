@@ -23,6 +23,8 @@
 // Algorithmic bytes per pillar: T*16 + 20 read per pass (+ units*4 of g in the backward).
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "lv_common.cuh"
 #include "lv_decorate.cuh"
 
@@ -374,3 +376,42 @@ extern "C" int lv_pillar_pfn_train_backward(lv_handle* h, const float* d_voxels,
   return LV_OK;
 }
 
+
+// ---------------------------------------------------------------- backward of PointPillarsScatter
+// d feats[p, c] = d canvas[b, c, y, x] for coords[p] = (b, ., y, x) (pointpillars.py:444-476 under autograd: the
+// transpose of `canvas[:, indices] = voxels`).  One warp per pillar, lane = channel: the reads are one 4-byte element
+// per channel plane (that is what the layout gives), the writes one coalesced row.  T = float or __half.
+template <typename T>
+__global__ void __launch_bounds__(256) pillar_gather_kernel(const T* __restrict__ grad, const int32_t* __restrict__ coords,
+                                                           int64_t P, int C, int B, int ny, int nx, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * 8;
+  const int64_t plane = (int64_t)ny * nx;
+  for (int64_t pil = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); pil < P; pil += warps) {
+    const int4 co = __ldg(reinterpret_cast<const int4*>(coords) + pil);   // b, z, y, x
+    const bool ok = co.x >= 0 && co.x < B && co.z >= 0 && co.z < ny && co.w >= 0 && co.w < nx;
+    const T* src = grad + ((int64_t)co.x * C) * plane + (int64_t)co.z * nx + co.w;
+    for (int c = lane; c < C; c += 32) out[pil * C + c] = ok ? src[(int64_t)c * plane] : T(0);
+  }
+}
+
+extern "C" int lv_pillar_scatter_backward(lv_handle* h, const void* d_grad_canvas, const int32_t* d_coords, int64_t n_pillars,
+                                          int32_t channels, int32_t batch_size, int32_t ny, int32_t nx, int32_t half,
+                                          void* d_grad_feats, lv_stream stream_) {
+  LV_REQUIRE(h != nullptr, "lv_pillar_scatter_backward: null handle");
+  LV_REQUIRE(n_pillars >= 0 && channels > 0 && batch_size >= 0 && ny > 0 && nx > 0, "lv_pillar_scatter_backward: bad sizes");
+  if (n_pillars == 0) return LV_OK;
+  LV_REQUIRE(d_grad_canvas && d_coords && d_grad_feats, "lv_pillar_scatter_backward: null pointer");
+  LV_REQUIRE((reinterpret_cast<uintptr_t>(d_coords) & 15) == 0, "lv_pillar_scatter_backward: coords must be 16-byte aligned");
+  LV_CHECK_CUDA(cudaSetDevice(h->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const unsigned blocks = (unsigned)std::min<int64_t>((int64_t)h->num_sms * 16, lv_div_up(n_pillars, 8));
+  if (half)
+    pillar_gather_kernel<__half><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __half*>(d_grad_canvas), d_coords, n_pillars,
+                                                              channels, batch_size, ny, nx, reinterpret_cast<__half*>(d_grad_feats));
+  else
+    pillar_gather_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(d_grad_canvas), d_coords, n_pillars,
+                                                             channels, batch_size, ny, nx, reinterpret_cast<float*>(d_grad_feats));
+  LV_LAUNCH_CHECK(h);
+  return LV_OK;
+}

@@ -369,15 +369,25 @@ class _ScatterFn(torch.autograd.Function):
             nat.check(fn(h.ptr, feats.data_ptr(), co.data_ptr(), P, C, batch_size, ny, nx,
                          canvas.data_ptr(), nat.current_stream_ptr(feats.device)))
         ctx.save_for_backward(co)
-        ctx.dims = (ny, nx)
+        ctx.dims = (batch_size, C, ny, nx)
         return canvas
 
     @staticmethod
     def backward(ctx, grad):
+        """d feats[p] = d canvas[b, :, y, x] (lv_pillar_scatter_backward)."""
         (co,) = ctx.saved_tensors
-        co = co.long()
-        g = grad[co[:, 0], :, co[:, 2], co[:, 3]]
-        return g, None, None, None, None
+        B, C, ny, nx = ctx.dims
+        lib = nat.load()
+        g = grad.contiguous()
+        if g.dtype not in (torch.float32, torch.float16):
+            g = g.float()
+        out = torch.empty((co.shape[0], C), dtype=g.dtype, device=g.device)
+        h = nat.get_handle(g.device.index)
+        with torch.cuda.device(g.device):
+            nat.check(lib.lv_pillar_scatter_backward(h.ptr, g.data_ptr(), co.data_ptr(), co.shape[0], C, B, ny, nx,
+                                                     int(g.dtype == torch.float16), out.data_ptr(),
+                                                     nat.current_stream_ptr(g.device)))
+        return out.to(grad.dtype), None, None, None, None
 
 
 def scatter_pillars(voxel_features, coords, batch_size, ny, nx):

@@ -162,8 +162,20 @@ def test_scatter_full_size_and_backward(pp, fixture_nx4):
     cells = rng.permutation(3 * 7 * 9)[:P]
     c2 = np.stack([cells // 63, np.zeros(P, np.int64), (cells % 63) // 9, cells % 9], 1).astype(np.int32)
     f2 = rng.normal(size=(P, 5)).astype(np.float32)
-    o2 = pp.scatter_pillars(_cuda(f2), _cuda(c2), 3, 7, 9)
-    assert np.array_equal(o2.cpu().numpy(), po.scatter(f2, c2, 3, 7, 9))
+    t2 = _cuda(f2).requires_grad_(True)
+    o2 = pp.scatter_pillars(t2, _cuda(c2), 3, 7, 9)
+    assert np.array_equal(o2.detach().cpu().numpy(), po.scatter(f2, c2, 3, 7, 9))
+    w2 = torch.randn_like(o2)
+    (o2 * w2).sum().backward()                              # lv_pillar_scatter_backward, C not a multiple of 32
+    c2l = torch.from_numpy(c2).long()
+    assert torch.equal(t2.grad.cpu(), w2.cpu()[c2l[:, 0], :, c2l[:, 2], c2l[:, 3]])
+    # float16 (apex O2): forward and backward in half
+    th = _cuda(feats).half().requires_grad_(True)
+    oh = mod(th, _cuda(coords), 2)
+    assert oh.dtype == torch.float16
+    wh = torch.randn_like(oh)
+    (oh * wh).sum().backward()
+    assert th.grad.dtype == torch.float16 and torch.equal(th.grad.cpu(), wh.cpu()[co[:, 0], :, co[:, 2], co[:, 3]])
     # empty input
     o3 = pp.scatter_pillars(_cuda(np.zeros((0, 64), np.float32)), _cuda(np.zeros((0, 4), np.int32)), 1, 400, 400)
     assert float(o3.abs().sum()) == 0.0
