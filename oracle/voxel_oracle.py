@@ -7,7 +7,12 @@ plus the output contract of second/second/data/preprocess.py:305-317.  The
 restatement IS pinned against that sibling: oracle/gen_golden.py executes the
 reference's ``points_to_bev`` on the bundled sweep and stores its density map;
 tests/test_oracle_voxel.py checks that this oracle's per-pillar counts and voxel
-count reproduce it (coordinate rule, bounds, first-come ids, ``break``).
+count reproduce it (coordinate rule, bounds, first-come ids, ``break``); five more
+cases at three-dimensional grids with the cap hit early (counts per column and the
+height of every (z, y, x) cell) come from oracle/gen_golden_simplevis3d.py, and
+tests/test_gpu_voxel.py holds the GPU voxelizer to the same goldens directly.  What
+stays unpinned is what only spconv knows: ``continue`` instead of ``break`` on
+overflow, and the order of the points inside a voxel.
 
 Two implementations of the same loop:
   * ``points_to_voxel_loop``  - pure Python, a line-for-line walk of the
